@@ -1,0 +1,121 @@
+/*
+ * kivi_b200.h -- C ABI of libkivi_b200.so, the B200-native (sm_100a) implementation of the
+ * KIVI decode hot path: 2/4-bit asymmetric pack of new K/V tokens and the batched dequant-GEMVs
+ * q.K^T and softmax.V over the packed cache (+ fp16 residual window).
+ *
+ * This is the drop-in boundary.  Each entry point replaces one interface of the reference
+ * (jy-yuan/KIVI @ 876b4d2); the reference-side binding a maintainer would add is shown in
+ * INTEGRATION.md.  Rules common to all entry points:
+ *   - plain C types only: device pointers, sizes, strides, a stream handle.  No torch types.
+ *   - the CALLER owns every buffer, outputs included; nothing is allocated, nothing is freed.
+ *   - asynchronous: work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and the call returns immediately.  No global state, re-entrant,
+ *     CUDA-graph capturable.  The device is the current device of the calling thread and must
+ *     own the pointers (the Python shim wraps calls in torch.cuda.device(tensor.device)).
+ *   - return 0 on success, a negative KIVI_ERR_* for argument errors (nothing was enqueued),
+ *     or a positive cudaError_t from the launch.  Never throws.
+ *   - fp16 data are IEEE binary16 (`__half` bits); packed codes are little-endian in the
+ *     32-bit word: element i of a word sits at bit i*bits (quant/new_pack.py:148-153).
+ */
+#ifndef KIVI_B200_H
+#define KIVI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KIVI_OK              0
+#define KIVI_ERR_BITS       -1   /* bits not in the supported set                         */
+#define KIVI_ERR_SHAPE      -2   /* a dimension / divisibility requirement is violated    */
+#define KIVI_ERR_GQA        -3   /* nh % nh_kv != 0 or nh_kv <= 0                         */
+#define KIVI_ERR_GROUP      -4   /* unsupported group_size                                */
+#define KIVI_ERR_ALIGN      -5   /* pointer / stride alignment requirement violated       */
+#define KIVI_ERR_NULL       -6   /* required pointer is NULL                              */
+#define KIVI_ERR_LAYOUT     -7   /* unknown layout id                                     */
+#define KIVI_ERR_CAPACITY   -8   /* cache capacity exceeded                               */
+#define KIVI_ERR_UNSUPPORTED -9  /* valid in the reference, not implemented by this build */
+
+#define KIVI_LAYOUT_REFERENCE 0  /* qB [U, K, N/fpi], scales/zeros [U, K, N/g]  (quant/matmul.py:189-191) */
+#define KIVI_LAYOUT_KERNEL    1  /* qB [U, N/fpi, K], scales/zeros [U, N/g, K]  (quant/csrc/gemv_cuda.cu:255-259) */
+
+/* Library identification. */
+int         kivi_version(void);
+const char* kivi_error_string(int code);
+/* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
+uint64_t    kivi_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Pack: asymmetric min/max quantisation along the LAST dim in groups of `group_size`,
+ * OR-packed into int32 words.
+ * Replaces triton_quantize_and_pack_along_last_dim(data, group_size, bit),
+ *   quant/new_pack.py:217-252 (Triton _minmax_along_last_dim :158-177, ATen chain :238-242,
+ *   Triton _pack_along_last_dim :132-154) -- one fused kernel instead of >= 9 launches.
+ * Bit-exact on codes, scale and mn (fp16 rounding chain of SURVEY 8 a1); degenerate group
+ * (mx == mn) -> code 0, scale 0.
+ *   x     [rows, T]       fp16, contiguous
+ *   code  [rows, T/fpi]   int32   (fpi = 32/bits)
+ *   scale [rows, T/g]     fp16
+ *   mn    [rows, T/g]     fp16
+ * Requires bits in {2,4,8}, T % group_size == 0 (quant/new_pack.py:222), T % fpi == 0.
+ * ------------------------------------------------------------------------------------------ */
+int kivi_pack_lastdim_f16(const void* x, int64_t rows, int64_t T, int group_size, int bits,
+                          void* code, void* scale, void* mn, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched "outer-dim" dequant-GEMV:  C[u_q, n] = sum_k A[u_q, k] * (scale*code + zero)[u_kv, k, n],
+ * u_kv = u_q / (nh / nh_kv); groups and packing run along n.  fp32 accumulate, fp16 store.
+ * Replaces
+ *   layout KIVI_LAYOUT_KERNEL   : kivi_gemv.gemv_forward_cuda_outer_dim(in, kernel, scales, zeros,
+ *                                 bit, group_size, nh, nh_kv), quant/csrc/gemv_cuda.h:12-20,
+ *                                 quant/csrc/gemv_cuda.cu:511-557 (+ kernels :265-427);
+ *   layout KIVI_LAYOUT_REFERENCE: the whole of cuda_bmm_fA_qB_outer, quant/matmul.py:178-219,
+ *                                 WITHOUT its three transpose().contiguous() copies (:205,213-214).
+ *   A      fp16, U_q = B*nh rows of K elements; row u at A + u*a_stride (elements), unit stride in k
+ *   qB     int32, U_kv = B*nh_kv units, unit u at qB + u*qb_unit_stride (words);
+ *            REFERENCE: word (k, n/fpi) at k*qb_row_stride + n/fpi
+ *            KERNEL   : word (n/fpi, k) at (n/fpi)*qb_row_stride + k
+ *   scales/zeros fp16, unit u at + u*sz_unit_stride (elements);
+ *            REFERENCE: (k, n/g) at k*sz_row_stride + n/g ;  KERNEL: (n/g, k) at (n/g)*sz_row_stride + k
+ *   C      fp16 [U_q, N] contiguous
+ * Requires bits in {2,4} (8 also accepted on KIVI_LAYOUT_REFERENCE, the Triton surface
+ * quant/matmul.py:112-175), nh % nh_kv == 0, group_size % fpi == 0, N % group_size == 0.
+ * (M, the number of query rows per head, is 1: the reference kernel ignores blockIdx.z,
+ *  quant/csrc/gemv_cuda.cu:538.)
+ * ------------------------------------------------------------------------------------------ */
+int kivi_bgemv_outer_f16(const void* A, int64_t a_stride,
+                         const void* qB, int64_t qb_unit_stride, int64_t qb_row_stride,
+                         const void* scales, const void* zeros, int64_t sz_unit_stride, int64_t sz_row_stride,
+                         void* C, int B, int nh, int nh_kv, int K, int N,
+                         int bits, int group_size, int layout, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Inner-dim (AWQ-style) GEMV: out[b, oc] = sum_ic in[b, ic] * (scale*code + zero)[oc, ic/g],
+ * packing and groups along ic.
+ * Replaces kivi_gemv.gemv_forward_cuda(in, kernel, scales, zeros, bit, group_size),
+ *   quant/csrc/gemv_cuda.h:4-10, quant/csrc/gemv_cuda.cu:201-246 (kernels :60-184; 4-bit only,
+ *   scales/zeros rows padded to sf_w = g64: ceil(ceil(IC/64/8)/2)*2*8, g128: ceil(IC/128/8)*8),
+ *   and the Triton gemv_fwd / gemv_kernel_g64 of quant/gemv.py:16-90 (any bit, sf_w = IC/g).
+ *   in [Bn, IC] fp16; kernel [OC, IC/fpi] int32; scales/zeros [OC, sf_w] fp16; out [Bn, OC] fp16.
+ * The reference silently returns uninitialised memory for group sizes other than 64/128
+ * (:227-245); here every group_size % fpi == 0 is computed.  IC % fpi == 0.
+ * ------------------------------------------------------------------------------------------ */
+int kivi_gemv_inner_f16(const void* in, const void* kernel, const void* scales, const void* zeros,
+                        void* out, int Bn, int IC, int OC, int bits, int group_size, int64_t sf_w,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Unpack + dequantise along the last dim in fp16: out = fp16(fp16(code * scale) + mn).
+ * Replaces unpack_and_dequant_vcache / unpack_and_dequant_kcache (quant/new_pack.py:51-83),
+ * the reference's own test oracle for the pack path.  bits in {2,4,8}.
+ *   code [rows, T/fpi] int32; scale, mn [rows, T/g] fp16; out [rows, T] fp16.
+ * ------------------------------------------------------------------------------------------ */
+int kivi_unpack_dequant_lastdim_f16(const void* code, const void* scale, const void* mn,
+                                    int64_t rows, int64_t T, int group_size, int bits,
+                                    void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KIVI_B200_H */

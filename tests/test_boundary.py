@@ -1,0 +1,114 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/kivi_b200.h declares, argument validation returns the documented codes without touching a
+GPU, the Python surface mirrors the reference's names/signatures, and the product never reaches
+into oracle/."""
+import inspect
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            txt = open(os.path.join(ROOT, "include", fn)).read()
+            txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+            names += re.findall(r"\b(kivi_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from kivi_b200 import build, _lib
+    build.build()                                                     # nvcc cross-compiles without a GPU
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(L):
+    syms = _declared_symbols()
+    assert len(syms) >= 7
+    for s in syms:
+        assert hasattr(L, s), f"libkivi_b200.so does not export {s} declared in include/kivi_b200.h"
+    assert L.kivi_version() >= 100
+
+
+def test_argument_validation_without_gpu(L):
+    """Every check happens before the first CUDA call, so the codes are observable on a CPU box."""
+    one = 16                                                          # a non-NULL dummy address, never dereferenced
+    assert L.kivi_pack_lastdim_f16(one, 4, 128, 32, 3, one, one, one, None) == -1          # bits
+    assert L.kivi_pack_lastdim_f16(one, 4, 100, 32, 2, one, one, one, None) == -2          # T % g   (new_pack.py:222)
+    assert L.kivi_pack_lastdim_f16(None, 4, 128, 32, 2, one, one, one, None) == -6         # NULL
+    assert L.kivi_pack_lastdim_f16(None, 0, 128, 32, 2, None, None, None, None) == 0       # empty is fine
+    assert L.kivi_bgemv_outer_f16(one, 128, one, 1, 1, one, one, 1, 1, one, 1, 3, 2, 128, 128, 2, 32, 0, None) == -3   # GQA
+    assert L.kivi_bgemv_outer_f16(one, 128, one, 1, 1, one, one, 1, 1, one, 1, 2, 2, 128, 128, 3, 32, 0, None) == -1   # bits
+    assert L.kivi_bgemv_outer_f16(one, 128, one, 1, 1, one, one, 1, 1, one, 1, 2, 2, 128, 100, 2, 32, 0, None) == -2   # N % g
+    assert L.kivi_bgemv_outer_f16(one, 128, one, 1, 1, one, one, 1, 1, one, 1, 2, 2, 128, 128, 8, 32, 1, None) == -1   # 8-bit only on ref layout
+    assert L.kivi_gemv_inner_f16(one, one, one, one, one, 1, 100, 8, 4, 64, 2, None) == -2                            # IC % fpi
+    assert L.kivi_error_string(-4).decode() == "unsupported group_size"
+
+
+def test_surface_mirrors_reference_names():
+    """Same function names and positional parameters as quant/new_pack.py, quant/matmul.py, quant/gemv.py
+    and the kivi_gemv extension."""
+    from kivi_b200 import gemv, kivi_gemv, matmul, new_pack
+    expect = {
+        (new_pack, "triton_quantize_and_pack_along_last_dim"): ["data", "group_size", "bit"],
+        (new_pack, "quant_and_pack_kcache"): ["k", "group_size", "bits"],
+        (new_pack, "quant_and_pack_vcache"): ["v", "group_size", "bits"],
+        (new_pack, "unpack_and_dequant_kcache"): ["k_code", "scale", "mn", "group_size", "bits"],
+        (new_pack, "unpack_and_dequant_vcache"): ["v_code", "scale", "mn", "group_size", "bits"],
+        (new_pack, "pack_tensor"): ["data", "bits", "pack_dim"],
+        (new_pack, "unpack_tensor"): ["v_code", "bits", "pack_dim"],
+        (matmul, "cuda_bmm_fA_qB_outer"): ["group_size", "fA", "qB", "scales", "zeros", "bits"],
+        (matmul, "triton_bmm_fA_qB_outer"): ["group_size", "fA", "qB", "scales", "zeros", "bits"],
+        (gemv, "gemv_fwd"): ["bit", "group_size", "inp", "qweight", "mn", "scale"],
+        (gemv, "dequant_weight"): ["w", "scale", "mn", "gs"],
+        (gemv, "dequant_weight_outer"): ["w", "scale", "mn", "gs"],
+        (kivi_gemv, "gemv_forward_cuda"): ["_in_feats", "_kernel", "_scaling_factors", "_zeros", "bit", "group_size"],
+        (kivi_gemv, "gemv_forward_cuda_outer_dim"): ["_in_feats", "_kernel", "_scaling_factors", "_zeros", "bit",
+                                                     "group_size", "nh", "nh_kv"],
+    }
+    for (mod, name), params in expect.items():
+        fn = getattr(mod, name)
+        assert list(inspect.signature(fn).parameters) == params, name
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: no file of the product package (or the include dir) may import,
+    load or execute anything under oracle/."""
+    pat = re.compile(r"(^\s*(from|import)\s+oracle\b)|(oracle[/\\._])|(kivi_oracle)", re.M)
+    for base in ("kivi_b200", "include", "quant", "models"):
+        d = os.path.join(ROOT, base)
+        if not os.path.isdir(d):
+            continue
+        for dp, _, files in os.walk(d):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    m = pat.search(txt)
+                    assert m is None or "never imports oracle" in txt.lower() or "Nothing in this package imports oracle" in txt, \
+                        f"{os.path.join(dp, fn)} references the oracle: {m.group(0)!r}"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from kivi_b200 import _lib
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    from kivi_b200 import matmul, new_pack
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        new_pack.triton_quantize_and_pack_along_last_dim(torch.zeros((1, 1, 2, 64), dtype=torch.float16), 32, 2)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        matmul.cuda_bmm_fA_qB_outer(32, torch.zeros((1, 1, 1, 8), dtype=torch.float16),
+                                    torch.zeros((1, 1, 8, 2), dtype=torch.int32),
+                                    torch.zeros((1, 1, 8, 1), dtype=torch.float16),
+                                    torch.zeros((1, 1, 8, 1), dtype=torch.float16), 2)
