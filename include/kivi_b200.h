@@ -115,6 +115,75 @@ int kivi_unpack_dequant_lastdim_f16(const void* code, const void* scale, const v
                                     int64_t rows, int64_t T, int group_size, int bits,
                                     void* out, void* stream);
 
+/* ==========================================================================================
+ * Pre-allocated KIVI cache + fused decode attention (the hot path of
+ * LlamaFlashAttention_KIVI.forward, models/llama_kivi.py:314-399, and its Mistral twin).
+ *
+ * The reference keeps a per-layer 9-tuple of tensors that it regrows with torch.cat every step
+ * (:350-352, :391-395, :454-455).  Here the caller allocates fixed buffers once (sizes from
+ * kivi_cache_sizes) and describes one LAYER's cache with a kivi_cache_t; `state` is a device
+ * int32[8] shared by all layers of a model {tk, r, tv, L, vhead, kv_len, -, -}: tk = tokens in the
+ * packed K store, r = tokens in the fp16 K window, tv = tokens in the packed V store, L = tokens in
+ * the fp16 V window (ring buffer starting at vhead).  All sequences of the batch have the same
+ * length, as in the reference (one kv_seq_len per cache, :309, :455).
+ * head_dim is 128 (every model the reference ships); group_size in {32,64,128};
+ * residual_length % group_size == 0 (:344) and <= 256.
+ * ========================================================================================== */
+typedef struct kivi_cache {
+    int32_t batch, num_heads, num_kv_heads, head_dim;
+    int32_t k_bits, v_bits, group_size, residual_length;
+    int32_t k_cap_blocks;   /* capacity of the K store in 128-token blocks   (kivi_cache_sizes out[0]) */
+    int32_t v_cap;          /* capacity of the V store in tokens             (out[1]) */
+    int32_t v_res_cap;      /* slots of the fp16 V ring buffer               (out[2]) */
+    int32_t reserved;
+    void* k_store;          /* out[3] bytes */
+    void* v_codes;          /* out[4] bytes */
+    void* v_meta;           /* out[5] bytes */
+    void* k_res;            /* out[6] bytes */
+    void* v_res;            /* out[7] bytes */
+    void* state;            /* device int32[8], shared by the layers of one model */
+} kivi_cache_t;
+
+/* Buffer sizes for a cache that can hold max_tokens tokens per sequence: out[0..2] = capacities
+ * (k_cap_blocks, v_cap, v_res_cap), out[3..7] = bytes of k_store, v_codes, v_meta, k_res, v_res. */
+int kivi_cache_sizes(int batch, int num_kv_heads, int k_bits, int v_bits, int group_size,
+                     int residual_length, int max_tokens, int64_t* out);
+
+/* Prefill: split + quantise the prompt's K/V exactly as models/llama_kivi.py:425-452 and set `state`.
+ *   k, v [B, Hkv, n, 128] fp16 contiguous (K after RoPE).  K: the first n - n%R tokens (all n if
+ *   R | n, none if n < R) are quantised per channel in groups of g tokens straight into the blocked
+ *   store (fused transpose + quantise); V: the first n - R tokens per token in groups of g channels. */
+int kivi_cache_prefill_f16(const kivi_cache_t* cache, const void* k, const void* v, int n, void* stream);
+
+/* One decode step of attention for one layer, fused (models/llama_kivi.py:314-399):
+ *   logits = [ q.Kq^T (dequantise in register) | q.K_full^T | q.k_new ]   each rounded to fp16 (:324-337)
+ *   s      = fp16(logits * (1/sqrt(128))) (+ mask, max with finfo.min)     (:339, :369-372)
+ *   p      = fp16(softmax_fp32(s))                                          (:375)
+ *   out    = fp16( fp16(p[:tv].Vq) + fp16(p[tv:].[V_full; v_new]) )         (:382-384)
+ * then, per unit, the cache data movement of :343-356 / :386-399: k_new joins the fp16 K window or,
+ * when that completes R tokens, the window is quantised into the K store; v_new joins the fp16 V
+ * ring and, once it holds more than R tokens, its oldest token is quantised into the V store.
+ * `state` is READ ONLY here; call kivi_cache_advance once per step after the last layer.
+ *   q [B, H, 128], k_new / v_new [B, Hkv, 128], out [B, H, 128]  fp16 contiguous
+ *   mask: NULL or additive fp16 [B, kv_len + 1] (broadcast over heads, :364-372)
+ *   dbg_logits / dbg_probs: NULL or fp16 [B, H, dbg_stride] receiving s and p (tests)
+ *   max_kv_len: upper bound of kv_len + 1 used to size shared memory (<= what the device allows,
+ *   else KIVI_ERR_CAPACITY).  Persistent grid: one CTA per SM looping over (b, kv-head) units;
+ *   packed tiles stream HBM -> shared memory through cp.async.bulk (TMA) into an mbarrier ring.  */
+int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const void* k_new, const void* v_new,
+                              const void* mask, void* out, void* dbg_logits, void* dbg_probs,
+                              int64_t dbg_stride, int max_kv_len, void* stream);
+
+/* Advance `state` by one token (the bookkeeping of :343-356, :386-399); once per step, all layers. */
+int kivi_cache_advance(const kivi_cache_t* cache, void* stream);
+
+/* Copy the cache out in the reference's 9-tuple layout (models/llama_kivi.py:454-455); lengths are
+ * passed by the host (it mirrors `state`).  k_code [U,128,tk/fpi] i32, k_scale/k_mn [U,128,tk/g],
+ * k_full [U,r,128], v_code [U,tv,128/fpi] i32, v_scale/v_mn [U,tv,128/g], v_full [U,L,128]. */
+int kivi_cache_export_f16(const kivi_cache_t* cache, int tk, int r, int tv, int L, int vhead,
+                          void* k_code, void* k_scale, void* k_mn, void* k_full,
+                          void* v_code, void* v_scale, void* v_mn, void* v_full, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

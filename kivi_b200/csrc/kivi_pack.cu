@@ -161,7 +161,7 @@ unpack_dequant_lastdim_kernel(const uint32_t* __restrict__ code, const __half* _
         const int64_t e = wid * FPI + j;
         const int64_t gid = e / g;
         const __half c = __float2half_rn((float)((w >> (BITS * j)) & ((1u << BITS) - 1u)));
-        out[e] = __hadd(__hmul(c, scale[gid]), mn[gid]);
+        out[e] = __hadd_rn(__hmul_rn(c, scale[gid]), mn[gid]);   // two roundings: no HFMA contraction
     }
 }
 

@@ -91,7 +91,37 @@ def main():
     res["ours_pack_k_flush_ms"] = ms
     res["ours_pack_k_flush_GBps"] = (kres.numel() * 2 * (1 + (bits / 8 + 4 / g) / 2)) / ms / 1e6
 
+    # fused decode attention on the blocked cache (one launch: qK + softmax + pV + cache update)
+    from kivi_b200.cache import KiviCache
+    del kc, ks, kz, vc, vs, vz
+    cache = KiviCache(1, B, H, Hkv, 128, bits, bits, g, R, max_tokens=T + 256)
+    nfill = T - 1 - R // 2                                            # mid-window state (no K flush in the timed call)
+    kk = torch.randn((B, Hkv, nfill, D), generator=gen, device=dev, dtype=torch.float16)
+    vv = torch.randn((B, Hkv, nfill, D), generator=gen, device=dev, dtype=torch.float16)
+    cache.prefill(0, kk, vv)
+    del kk, vv
+    qd = torch.randn((B, H, D), generator=gen, device=dev, dtype=torch.float16)
+    kn = torch.randn((B, Hkv, D), generator=gen, device=dev, dtype=torch.float16)
+    vn = torch.randn((B, Hkv, D), generator=gen, device=dev, dtype=torch.float16)
+    outd = torch.empty_like(qd)
+    per_tok = D * (bits / 8 + 4 / g)
+    bytes_fused = B * Hkv * (cache.tk * per_tok + cache.tv * per_tok + (cache.r + cache.L) * D * 2) + 2 * B * H * D * 2
+    ms, best = timeit(lambda: cache.decode_attention(0, qd, kn, vn, out=outd), flush=flush, iters=30)
+    res["fused_state"] = [cache.tk, cache.r, cache.tv, cache.L]
+    res["fused_decode_ms"] = ms
+    res["fused_decode_best_ms"] = best
+    res["fused_decode_GBps"] = bytes_fused / ms / 1e6
+    res["fused_bytes"] = bytes_fused
+    ms2, _ = timeit(lambda: cache.decode_attention(0, qd, kn, vn, out=outd), iters=30)   # no L2 flush (cache >> L2 anyway)
+    res["fused_decode_noflush_ms"] = ms2
+
     if a.ref:
+        kT = torch.randn((B, Hkv, D, Tk), generator=gen, device=dev, dtype=torch.float16)
+        kc, ks, kz = new_pack.triton_quantize_and_pack_along_last_dim(kT, g, bits)
+        del kT
+        v = torch.randn((B, Hkv, Tv, D), generator=gen, device=dev, dtype=torch.float16)
+        vc, vs, vz = new_pack.triton_quantize_and_pack_along_last_dim(v, g, bits)
+        del v
         from oracle import build_ref
         refmod = build_ref.load()
         if refmod is None:
