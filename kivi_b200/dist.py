@@ -1,0 +1,85 @@
+"""Multi-GPU decode: data-parallel replicas over the batch, one all-gather of the logits per step.
+
+Every (b, kv-head) unit of the KIVI hot path is independent, so the batch is sharded in
+contiguous ranges, each rank runs the whole model on its shard with NO per-layer collective, and the
+only exchange is one all-gather of the final logits [B/N, vocab] at the sampling step (NCCL over
+NVLink 5 / NVSwitch on GPUs, gloo on CPU for the tests), followed by identical sampling on every rank.
+The reference has nothing here (device_map="auto" layer placement only).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment (1 process per GPU)."""
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0)))
+
+
+def init(backend: str | None = None):
+    rank, ws, local = world()
+    if ws > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=ws, **kw)
+    return rank, ws, local
+
+
+def shard_range(global_batch: int, rank: int, world_size: int):
+    """Contiguous batch range [lo, hi) of `rank`; sizes differ by at most one."""
+    base, rem = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_logits(local_logits: torch.Tensor, global_batch: int | None = None) -> torch.Tensor:
+    """All-gather [B_local, vocab] -> [B_global, vocab] (rank order = batch order)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_logits
+    ws = dist.get_world_size()
+    if global_batch is None or global_batch % ws == 0:
+        out = torch.empty((ws * local_logits.shape[0],) + local_logits.shape[1:], dtype=local_logits.dtype,
+                          device=local_logits.device)
+        dist.all_gather_into_tensor(out, local_logits.contiguous())
+        return out
+    # ragged shards: pad every shard to the largest one, gather, drop the padding
+    sizes = [hi - lo for lo, hi in (shard_range(global_batch, r, ws) for r in range(ws))]
+    mx = max(sizes)
+    padded = torch.zeros((mx,) + local_logits.shape[1:], dtype=local_logits.dtype, device=local_logits.device)
+    padded[: local_logits.shape[0]] = local_logits
+    out = torch.empty((ws * mx,) + local_logits.shape[1:], dtype=local_logits.dtype, device=local_logits.device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * mx: r * mx + n] for r, n in enumerate(sizes)], 0)
+
+
+def greedy_next_tokens(local_logits: torch.Tensor, rank: int, world_size: int, global_batch: int):
+    """The sampling step: gather the logits of all shards, take the argmax on every rank (identical result),
+    return (all tokens [B_global], this rank's tokens [B_local])."""
+    full = gather_logits(local_logits, global_batch)
+    toks = full.argmax(-1)
+    lo, hi = shard_range(global_batch, rank, world_size)
+    return toks, toks[lo:hi]
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def max_over_ranks(x: float, device=None) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device if device is not None else "cpu")
+    if dist.get_backend() == "nccl":
+        t = t.to(torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,415 @@
+"""Drop-in surface of the reference's models/llama_kivi.py (and, by config, models/mistral_kivi.py).
+
+* `kivi_decode_attention_tuple`  -- the decode branch of LlamaFlashAttention_KIVI.forward
+  (models/llama_kivi.py:314-399) on the reference's own 9-tuple cache, op for op, with every KIVI op
+  routed to libkivi_b200 (cuda_bmm_fA_qB_outer without re-layout copies, fused pack kernel).
+* `kivi_prefill_tuple`           -- the prefill split + pack (:425-455) producing that 9-tuple.
+* `LlamaFlashAttention_KIVI`     -- attention module: same projections / RoPE / cache policy; the fast
+  path keeps the cache in a pre-allocated `KiviCache` and runs ONE fused CUDA launch per layer per
+  step (kivi_decode.cu); `past_key_value` may also be the legacy 9-tuple (then the tuple path runs).
+* `LlamaForCausalLM_KIVI`        -- decoder-only LM with HF Llama parameter names (state dicts of
+  LlamaForCausalLM / MistralForCausalLM load unchanged), config attrs k_bits, v_bits, group_size,
+  residual_length (models/llama_kivi.py:34-38).  Host code is PyTorch (linears = cuBLAS); the decode
+  step is captured in a CUDA graph.
+
+The reference's forks star-import transformers 4.43 internals and do not import under the installed
+transformers 5.5; this module depends on torch only and accepts any config object with the
+usual Llama fields.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .cache import KiviCache
+from .matmul import cuda_bmm_fA_qB_outer
+from .new_pack import triton_quantize_and_pack_along_last_dim
+
+
+def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
+    """transformers' repeat_kv, used by the reference at models/llama_kivi.py:337,384."""
+    if n_rep == 1:
+        return hidden_states
+    b, h, t, d = hidden_states.shape
+    return hidden_states[:, :, None, :, :].expand(b, h, n_rep, t, d).reshape(b, h * n_rep, t, d)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's cache policy on its own 9-tuple (functional form of the hook)
+# ---------------------------------------------------------------------------------------------------
+def _cat(old, new, dim):
+    return new if old is None else torch.cat([old, new], dim=dim)
+
+
+def kivi_prefill_tuple(key_states, value_states, group_size, k_bits, v_bits, residual_length):
+    """Prefill split + pack of models/llama_kivi.py:425-455: key/value_states [B, Hkv, n, D] -> 9-tuple.
+    K: the leading n - n % R tokens are packed per channel (none if n < R), the rest stays fp16;
+    V: everything but the newest R tokens is packed per token."""
+    n, R = key_states.shape[-2], residual_length
+    n_kq = n - n % R if n >= R else 0
+    k_code = k_scale = k_mn = None
+    if n_kq:
+        k_code, k_scale, k_mn = triton_quantize_and_pack_along_last_dim(
+            key_states[:, :, :n_kq].transpose(2, 3).contiguous(), group_size, k_bits)
+    k_full = key_states[:, :, n_kq:].contiguous() if n_kq < n else None
+    n_vq = max(n - R, 0)
+    v_code = v_scale = v_mn = None
+    if n_vq:
+        v_code, v_scale, v_mn = triton_quantize_and_pack_along_last_dim(value_states[:, :, :n_vq].contiguous(),
+                                                                        group_size, v_bits)
+    v_full = value_states[:, :, n_vq:].contiguous() if n_vq else value_states
+    return (k_code, k_full, k_scale, k_mn, v_code, v_full, v_scale, v_mn, n)
+
+
+def kivi_decode_attention_tuple(query_states, key_states, value_states, past_key_value, group_size, k_bits, v_bits,
+                                residual_length, attention_mask=None):
+    """Decode branch of the reference hook (models/llama_kivi.py:314-399, tuple :454-455) on the
+    reference's own 9-tuple, with the same rounding points; every KIVI op runs in libkivi_b200.
+    query_states [B,H,1,D], key/value_states [B,Hkv,1,D] (post-RoPE) -> (attn_output [B,H,1,D], new 9-tuple)."""
+    k_code, k_full, k_scale, k_mn, v_code, v_full, v_scale, v_mn, seen = past_key_value
+    B, H, q_len, D = query_states.shape
+    rep = H // key_states.shape[1]
+    R = residual_length
+    total = seen + key_states.shape[-2]
+
+    # logits = [ q . dequant(K_packed)^T | q . K_window^T ] / sqrt(D)            (:323-341)
+    k_full = _cat(k_full, key_states, 2)
+    pieces = []
+    if k_code is not None:
+        pieces.append(cuda_bmm_fA_qB_outer(group_size, query_states, k_code, k_scale, k_mn, k_bits))
+    pieces.append(torch.matmul(query_states, repeat_kv(k_full, rep).transpose(2, 3)))
+    scores = (torch.cat(pieces, dim=-1) if len(pieces) > 1 else pieces[0]) / math.sqrt(D)
+    if scores.shape != (B, H, q_len, total):                                     # (:358-362)
+        raise ValueError(f"Attention weights should be of size {(B, H, q_len, total)}, but is {tuple(scores.shape)}")
+
+    # a full window is packed per channel and appended along the token axis      (:343-356)
+    if k_full.shape[-2] == R:
+        assert R % group_size == 0
+        c, sc, mn = triton_quantize_and_pack_along_last_dim(k_full.transpose(2, 3).contiguous(), group_size, k_bits)
+        k_code, k_scale, k_mn, k_full = _cat(k_code, c, 3), _cat(k_scale, sc, 3), _cat(k_mn, mn, 3), None
+
+    if attention_mask is not None:                                               # (:364-372)
+        if attention_mask.shape != (B, 1, q_len, total):
+            raise ValueError(f"Attention mask should be of size {(B, 1, q_len, total)}, but is {tuple(attention_mask.shape)}")
+        floor = torch.tensor(torch.finfo(scores.dtype).min, device=scores.device)
+        scores = torch.max(scores + attention_mask, floor)
+    probs = F.softmax(scores, dim=-1, dtype=torch.float32).to(query_states.dtype)   # (:375)
+
+    # out = probs[:tv] . dequant(V_packed) + probs[tv:] . V_window                  (:377-384)
+    v_full = _cat(v_full, value_states, 2)
+    L = v_full.shape[-2]
+    window_part = torch.matmul(probs[..., -L:], repeat_kv(v_full, rep))
+    if v_code is None:
+        attn_output = window_part
+    else:
+        attn_output = cuda_bmm_fA_qB_outer(group_size, probs[..., :-L], v_code, v_scale, v_mn, v_bits)
+        attn_output += window_part
+
+    # the window keeps R tokens: its oldest one is packed per token                  (:386-399)
+    if L > R:
+        assert L == R + 1
+        c, sc, mn = triton_quantize_and_pack_along_last_dim(v_full[:, :, :1].contiguous(), group_size, v_bits)
+        v_code, v_scale, v_mn = _cat(v_code, c, 2), _cat(v_scale, sc, 2), _cat(v_mn, mn, 2)
+        v_full = v_full[:, :, 1:].contiguous()
+    return attn_output, (k_code, k_full, k_scale, k_mn, v_code, v_full, v_scale, v_mn, total)
+
+
+# ---------------------------------------------------------------------------------------------------
+# model
+# ---------------------------------------------------------------------------------------------------
+def default_config(name: str = "llama-2-7b", **kw):
+    """Architecture shapes of the BASELINE configs (weights are random-init; no checkpoints offline)."""
+    table = {
+        "llama-2-7b": dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+                           num_key_value_heads=32, vocab_size=32000, rope_theta=10000.0, rms_norm_eps=1e-5),
+        "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                           num_key_value_heads=8, vocab_size=128256, rope_theta=500000.0, rms_norm_eps=1e-5),
+        "mistral-7b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                           num_key_value_heads=8, vocab_size=32000, rope_theta=1000000.0, rms_norm_eps=1e-5),
+        "tiny": dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                     num_key_value_heads=2, vocab_size=512, rope_theta=10000.0, rms_norm_eps=1e-5),
+    }
+    cfg = dict(table[name], k_bits=2, v_bits=2, group_size=32, residual_length=128, use_flash=True,
+               max_position_embeddings=32768 + 1024)
+    cfg.update(kw)
+    return SimpleNamespace(**cfg)
+
+
+class LlamaRMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        return F.rms_norm(x, (x.shape[-1],), self.weight, self.variance_epsilon)
+
+
+def _rope_tables(head_dim, max_pos, theta, device):
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=device) / head_dim))
+    freqs = torch.outer(torch.arange(max_pos, dtype=torch.float32, device=device), inv_freq)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().half(), emb.sin().half()
+
+
+def _rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+class LlamaFlashAttention_KIVI(nn.Module):
+    """Attention layer of the reference (models/llama_kivi.py:264-466), KIVI ops on libkivi_b200."""
+
+    def __init__(self, config, layer_idx: int = 0):
+        super().__init__()
+        self.config = config
+        self.layer_idx = layer_idx
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.head_dim = self.hidden_size // self.num_heads
+        self.num_key_value_heads = config.num_key_value_heads
+        self.num_key_value_groups = self.num_heads // self.num_key_value_heads
+        self.k_bits, self.v_bits = config.k_bits, config.v_bits            # models/llama_kivi.py:34-38
+        self.group_size, self.residual_length = config.group_size, config.residual_length
+        bias = getattr(config, "attention_bias", False)
+        self.q_proj = nn.Linear(self.hidden_size, self.num_heads * self.head_dim, bias=bias)
+        self.k_proj = nn.Linear(self.hidden_size, self.num_key_value_heads * self.head_dim, bias=bias)
+        self.v_proj = nn.Linear(self.hidden_size, self.num_key_value_heads * self.head_dim, bias=bias)
+        self.o_proj = nn.Linear(self.num_heads * self.head_dim, self.hidden_size, bias=bias)
+
+    def _qkv(self, hidden_states, cos, sin):
+        bsz, q_len, _ = hidden_states.shape
+        q = self.q_proj(hidden_states).view(bsz, q_len, self.num_heads, self.head_dim).transpose(1, 2)
+        k = self.k_proj(hidden_states).view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+        v = self.v_proj(hidden_states).view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+        q = q * cos + _rotate_half(q) * sin                                 # apply_rotary_pos_emb (:311)
+        k = k * cos + _rotate_half(k) * sin
+        return q, k, v
+
+    def forward(self, hidden_states, cos, sin, past_key_value=None, attention_mask=None):
+        """hidden_states [B, q_len, hidden]; cos/sin broadcastable to [B, 1, q_len, D].
+        past_key_value: None (prefill, returns a 9-tuple), a 9-tuple (reference semantics), or a
+        (KiviCache, layer) pair (fused path; prefill fills it, decode is one launch)."""
+        bsz, q_len, _ = hidden_states.shape
+        q, k, v = self._qkv(hidden_states, cos, sin)
+        fused = isinstance(past_key_value, tuple) and len(past_key_value) == 2 and isinstance(past_key_value[0], KiviCache)
+        if fused:
+            cache, layer = past_key_value
+            if q_len > 1:                                                   # prefill (:401-452)
+                attn_output = F.scaled_dot_product_attention(q, repeat_kv(k, self.num_key_value_groups),
+                                                             repeat_kv(v, self.num_key_value_groups), is_causal=True)
+                cache.prefill(layer, k, v)
+                attn_output = attn_output.transpose(1, 2).reshape(bsz, q_len, self.hidden_size)
+            else:                                                           # decode (:314-399), one launch
+                out = cache.decode_attention(layer, q.reshape(bsz, self.num_heads, self.head_dim).contiguous(),
+                                             k.reshape(bsz, self.num_key_value_heads, self.head_dim).contiguous(),
+                                             v.reshape(bsz, self.num_key_value_heads, self.head_dim).contiguous(),
+                                             mask=attention_mask)
+                attn_output = out.view(bsz, 1, self.hidden_size)
+            return self.o_proj(attn_output), None, past_key_value
+        if past_key_value is not None:                                      # reference 9-tuple, decode
+            attn_output, past = kivi_decode_attention_tuple(q, k, v, past_key_value, self.group_size, self.k_bits,
+                                                            self.v_bits, self.residual_length, attention_mask)
+            attn_output = attn_output.transpose(1, 2).contiguous()
+        else:                                                               # prefill -> 9-tuple
+            attn_output = F.scaled_dot_product_attention(q, repeat_kv(k, self.num_key_value_groups),
+                                                         repeat_kv(v, self.num_key_value_groups), is_causal=True)
+            attn_output = attn_output.transpose(1, 2)
+            past = kivi_prefill_tuple(k, v, self.group_size, self.k_bits, self.v_bits, self.residual_length)
+        attn_output = attn_output.reshape(bsz, q_len, self.hidden_size)
+        return self.o_proj(attn_output), None, past
+
+
+LlamaAttention_KIVI = LlamaFlashAttention_KIVI      # models/llama_kivi.py:19 (unreachable in the reference: ctor asserts use_flash)
+
+
+class LlamaMLP(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.gate_proj = nn.Linear(config.hidden_size, config.intermediate_size, bias=False)
+        self.up_proj = nn.Linear(config.hidden_size, config.intermediate_size, bias=False)
+        self.down_proj = nn.Linear(config.intermediate_size, config.hidden_size, bias=False)
+
+    def forward(self, x):
+        return self.down_proj(F.silu(self.gate_proj(x)) * self.up_proj(x))
+
+
+class LlamaDecoderLayer_KIVI(nn.Module):
+    def __init__(self, config, layer_idx):
+        super().__init__()
+        self.self_attn = LlamaFlashAttention_KIVI(config, layer_idx)
+        self.mlp = LlamaMLP(config)
+        self.input_layernorm = LlamaRMSNorm(config.hidden_size, config.rms_norm_eps)
+        self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, config.rms_norm_eps)
+
+    def forward(self, hidden_states, cos, sin, past_key_value=None, attention_mask=None):
+        residual = hidden_states
+        h, _, past = self.self_attn(self.input_layernorm(hidden_states), cos, sin, past_key_value, attention_mask)
+        hidden_states = residual + h
+        hidden_states = hidden_states + self.mlp(self.post_attention_layernorm(hidden_states))
+        return hidden_states, past
+
+
+class LlamaModel_KIVI(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size)
+        self.layers = nn.ModuleList([LlamaDecoderLayer_KIVI(config, i) for i in range(config.num_hidden_layers)])
+        self.norm = LlamaRMSNorm(config.hidden_size, config.rms_norm_eps)
+
+
+class LlamaForCausalLM_KIVI(nn.Module):
+    """models/llama_kivi.py:785.  `decode_step` / `generate` use the fused cache path; `forward` keeps the
+    reference's (logits, past_key_values) contract with the legacy per-layer 9-tuples."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.model = LlamaModel_KIVI(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self._rope = None
+        self.cache: KiviCache | None = None
+        self._graph = None
+
+    # ------------------------------------------------------------------ helpers
+    def _tables(self, device):
+        if self._rope is None or self._rope[0].device != device:
+            hd = self.config.hidden_size // self.config.num_attention_heads
+            self._rope = _rope_tables(hd, self.config.max_position_embeddings, self.config.rope_theta, device)
+        return self._rope
+
+    def _run_layers(self, input_ids, positions, pasts, attention_mask=None):
+        cos_t, sin_t = self._tables(input_ids.device)
+        cos = cos_t.index_select(0, positions.reshape(-1)).view(positions.shape[0], 1, positions.shape[1], -1)
+        sin = sin_t.index_select(0, positions.reshape(-1)).view(positions.shape[0], 1, positions.shape[1], -1)
+        h = self.model.embed_tokens(input_ids)
+        new_pasts = []
+        for i, layer in enumerate(self.model.layers):
+            h, past = layer(h, cos, sin, pasts[i] if pasts is not None else None, attention_mask)
+            new_pasts.append(past)
+        h = self.model.norm(h)
+        return h, new_pasts
+
+    # ------------------------------------------------------------------ reference-style forward (9-tuples)
+    @torch.no_grad()
+    def forward(self, input_ids, past_key_values=None, attention_mask=None):
+        """Returns (logits [B, q_len, vocab] fp32, past_key_values): per-layer 9-tuples as in the reference
+        (models/llama_kivi.py:696-698, :911-916).  Prefill when past_key_values is None."""
+        B, q_len = input_ids.shape
+        start = 0 if past_key_values is None else past_key_values[0][-1]
+        positions = torch.arange(start, start + q_len, device=input_ids.device).unsqueeze(0).expand(B, -1)
+        h, pasts = self._run_layers(input_ids, positions, past_key_values, attention_mask)
+        return self.lm_head(h).float(), pasts                                # logits.float() (:881)
+
+    # ------------------------------------------------------------------ fused cache path
+    def init_cache(self, batch: int, max_tokens: int):
+        cfg = self.config
+        dev = self.lm_head.weight.device
+        self.cache = KiviCache(cfg.num_hidden_layers, batch, cfg.num_attention_heads, cfg.num_key_value_heads,
+                               cfg.hidden_size // cfg.num_attention_heads, cfg.k_bits, cfg.v_bits, cfg.group_size,
+                               cfg.residual_length, max_tokens, device=dev)
+        self._graph = None
+        self._pos = torch.zeros((batch, 1), dtype=torch.long, device=dev)
+        self._ids = torch.zeros((batch, 1), dtype=torch.long, device=dev)
+        self._logits = torch.zeros((batch, cfg.vocab_size), dtype=torch.float32, device=dev)
+        return self.cache
+
+    @torch.no_grad()
+    def prefill(self, input_ids):
+        """Run the prompt, fill the cache (models/llama_kivi.py:401-452), return last-position logits."""
+        assert self.cache is not None, "call init_cache() first"
+        B, n = input_ids.shape
+        positions = torch.arange(n, device=input_ids.device).unsqueeze(0).expand(B, -1)
+        pasts = [(self.cache, i) for i in range(len(self.model.layers))]
+        h, _ = self._run_layers(input_ids, positions, pasts)
+        self._pos.fill_(n)
+        return self.lm_head(h[:, -1]).float()
+
+    @torch.no_grad()
+    def prefill_synthetic(self, n: int, seed: int = 0):
+        """Fill every layer's cache with n random K/V tokens (benchmarks: the prompt's attention itself is
+        off the decode hot path; the cache contents are produced by the real prefill pack kernels)."""
+        assert self.cache is not None
+        c = self.cache
+        gen = torch.Generator(device=c.device).manual_seed(seed)
+        for l in range(c.n_layers):
+            k = torch.randn((c.batch, c.num_kv_heads, n, c.head_dim), generator=gen, device=c.device, dtype=torch.float16)
+            v = torch.randn((c.batch, c.num_kv_heads, n, c.head_dim), generator=gen, device=c.device, dtype=torch.float16)
+            c.prefill(l, k, v)
+        self._pos.fill_(n)
+
+    def _step_body(self):
+        pasts = [(self.cache, i) for i in range(len(self.model.layers))]
+        h, _ = self._run_layers(self._ids, self._pos, pasts)
+        self._logits.copy_(self.lm_head(h[:, 0]).float())
+        self.cache_advance_device()
+        self._pos.add_(1)
+
+    def cache_advance_device(self):
+        from . import _lib
+        import ctypes
+        with torch.cuda.device(self.cache.device):
+            _lib.check(_lib.lib().kivi_cache_advance(ctypes.byref(self.cache._structs[0]),
+                                                     _lib.stream_ptr(self.cache.device)), "kivi_cache_advance")
+
+    @torch.no_grad()
+    def decode_step(self, input_ids=None, use_graph: bool = True):
+        """One decode step for the whole batch: input_ids [B, 1] (device) -> logits [B, vocab] fp32 (device,
+        a static buffer).  The step (32 x [norm, qkv, rope, fused KIVI attention, o_proj, MLP], lm_head,
+        cache advance) is captured once in a CUDA graph and replayed."""
+        assert self.cache is not None
+        if self.cache.kv_len + 1 > self.cache.max_tokens:
+            raise ValueError("KIVI cache capacity exceeded")
+        if input_ids is not None:
+            self._ids.copy_(input_ids.view(-1, 1))
+        if not use_graph:
+            self._step_body()
+        else:
+            if self._graph is None:
+                # warm-up on a side stream (cuBLAS workspaces, lazy module loading), then capture
+                state = self.cache.state.clone()
+                pos = self._pos.clone()
+                snap = [[b.clone() for b in (bufs[3], bufs[4])] for bufs in self.cache._bufs]  # fp16 windows
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._step_body()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                # undo the warm-up step's effect on the lengths (data it wrote lies beyond them)
+                self.cache.state.copy_(state)
+                self._pos.copy_(pos)
+                for bufs, (kr, vr) in zip(self.cache._bufs, snap):
+                    bufs[3].copy_(kr)
+                    bufs[4].copy_(vr)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body()
+                # capture does not execute: state is still the pre-step state
+                self._graph = g
+            self._graph.replay()
+        self.cache._mirror_advance()
+        return self._logits
+
+    @torch.no_grad()
+    def generate(self, input_ids, max_new_tokens: int, use_graph: bool = True):
+        """Greedy decoding (the reference goes through HF generate; sampling is outside the hot path)."""
+        B, n = input_ids.shape
+        if self.cache is None:
+            self.init_cache(B, n + max_new_tokens)
+        logits = self.prefill(input_ids)
+        out = [input_ids]
+        tok = logits.argmax(-1, keepdim=True)
+        for _ in range(max_new_tokens):
+            out.append(tok)
+            logits = self.decode_step(tok, use_graph=use_graph)
+            tok = logits.argmax(-1, keepdim=True)
+        return torch.cat(out, dim=1)
+
+
+MistralForCausalLM_KIVI = LlamaForCausalLM_KIVI       # models/mistral_kivi.py:921 -- same hook; GQA is handled in-kernel
+MistralFlashAttention_KIVI = LlamaFlashAttention_KIVI  # (no repeat_kv_quant copies, models/mistral_kivi.py:58-67)
