@@ -191,6 +191,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     # our launches per captured step = launches enqueued while capturing (the graph replays them)
     launches_per_step = cfg.num_hidden_layers + 1
+    if os.environ.get("KIVI_PROFILE_STEPS"):                 # ncu --profile-from-start off: profile N steps, exit
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(int(os.environ["KIVI_PROFILE_STEPS"])):
+            ids = step(ids)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
     sampler = ClockSampler(local)
     kdist.barrier()
     torch.cuda.synchronize()
