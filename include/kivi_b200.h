@@ -184,6 +184,20 @@ int kivi_cache_export_f16(const kivi_cache_t* cache, int tk, int r, int tv, int 
                           void* k_code, void* k_scale, void* k_mn, void* k_full,
                           void* v_code, void* v_scale, void* v_mn, void* v_full, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Glue kernels of the decode step around the hot path (not part of the KIVI operators; they
+ * replace ~16 ATen elementwise launches per layer per step in kivi_b200/llama_kivi.py).  fp16 I/O,
+ * arithmetic of the HF Llama modules the reference forks: every fp16 op rounds to fp16.
+ *   kivi_add_rmsnorm_f16 : residual += x (x may be NULL); out = weight * fp16(residual * rsqrt(mean(residual^2)+eps))
+ *   kivi_rope_split_f16  : qkv [B,(H+2Hkv)*128] -> q [B,H,128], k [B,Hkv,128] (rotary at position pos[b], int64), v
+ *   kivi_silu_mul_f16    : gate_up [rows, 2*I] -> out [rows, I] = fp16(silu(gate)) * up
+ * ------------------------------------------------------------------------------------------ */
+int kivi_add_rmsnorm_f16(const void* x, void* residual, const void* weight, void* out,
+                         int rows, int hidden, float eps, void* stream);
+int kivi_rope_split_f16(const void* qkv, const void* cos_table, const void* sin_table, const void* pos,
+                        void* q, void* k, void* v, int batch, int num_heads, int num_kv_heads, void* stream);
+int kivi_silu_mul_f16(const void* gate_up, void* out, int rows, int intermediate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

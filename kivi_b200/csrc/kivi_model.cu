@@ -1,0 +1,117 @@
+// kivi_model.cu -- small fused glue kernels of the decode step around the hot path (sm_100a):
+// residual-add + RMSNorm, RoPE + q/k/v split, SiLU*mul.  They replace ~16 ATen elementwise launches per
+// layer per step with 4; arithmetic follows the HF Llama modules the reference forks
+// (models/llama_kivi.py star-imports transformers.models.llama): every fp16 op rounds to fp16.
+#include "kivi_common.cuh"
+
+namespace kivi {
+
+// residual (fp16, in/out) += x;  out = weight * fp16( residual * rsqrt(mean(residual^2) + eps) )
+// (LlamaRMSNorm.forward: fp32 statistics, cast to fp16, then multiply by the fp16 weight)
+template <bool ADD>
+__global__ void __launch_bounds__(256)
+add_rmsnorm_kernel(const __half* __restrict__ x, __half* __restrict__ residual, const __half* __restrict__ w,
+                   __half* __restrict__ out, int hidden, float eps)
+{
+    extern __shared__ float buf[];                       // hidden floats
+    __shared__ float red[8];
+    const int row = blockIdx.x;
+    __half* r = residual + (int64_t)row * hidden;
+    float ss = 0.f;
+    for (int i = threadIdx.x * 2; i < hidden; i += blockDim.x * 2) {
+        __half2 v = *reinterpret_cast<const __half2*>(r + i);
+        if (ADD) {
+            v = __hadd2_rn(v, *reinterpret_cast<const __half2*>(x + (int64_t)row * hidden + i));
+            *reinterpret_cast<__half2*>(r + i) = v;
+        }
+        const float2 f = __half22float2(v);
+        buf[i] = f.x; buf[i + 1] = f.y;
+        ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float rs = rsqrtf(tot / (float)hidden + eps);
+    for (int i = threadIdx.x * 2; i < hidden; i += blockDim.x * 2) {
+        const __half2 n = __floats2half2_rn(buf[i] * rs, buf[i + 1] * rs);
+        *reinterpret_cast<__half2*>(out + (int64_t)row * hidden + i) = __hmul2_rn(*reinterpret_cast<const __half2*>(w + i), n);
+    }
+}
+
+// qkv [B, (H + 2*Hkv) * 128] -> q [B,H,128], k [B,Hkv,128] (both rotated), v [B,Hkv,128]
+// apply_rotary_pos_emb: x*cos + rotate_half(x)*sin, each op rounded to fp16; cos/sin rows = position pos[b]
+__global__ void __launch_bounds__(64)
+rope_split_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos_t, const __half* __restrict__ sin_t,
+                  const long long* __restrict__ pos, __half* __restrict__ q, __half* __restrict__ k, __half* __restrict__ v,
+                  int H, int Hkv)
+{
+    constexpr int D = 128;
+    const int b = blockIdx.y, head = blockIdx.x, i = threadIdx.x;            // i < 64: pair (i, i + 64)
+    const __half* src = qkv + ((int64_t)b * (H + 2 * Hkv) + head) * D;
+    if (head >= H + Hkv) {                                                   // v: plain copy
+        __half* dst = v + ((int64_t)b * Hkv + head - H - Hkv) * D;
+        dst[i] = src[i]; dst[i + 64] = src[i + 64];
+        return;
+    }
+    const long long p = pos[b];
+    const __half c0 = cos_t[p * D + i], c1 = cos_t[p * D + i + 64];
+    const __half s0 = sin_t[p * D + i], s1 = sin_t[p * D + i + 64];
+    const __half x0 = src[i], x1 = src[i + 64];
+    __half* dst = head < H ? q + ((int64_t)b * H + head) * D : k + ((int64_t)b * Hkv + head - H) * D;
+    dst[i] = __hadd_rn(__hmul_rn(x0, c0), __hmul_rn(__hneg(x1), s0));       // rotate_half: (-x2, x1)
+    dst[i + 64] = __hadd_rn(__hmul_rn(x1, c1), __hmul_rn(x0, s1));
+}
+
+// gu [rows, 2*I] (gate | up) -> out [rows, I] = fp16(silu(gate)) * up
+__global__ void __launch_bounds__(256)
+silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int I)
+{
+    const int row = blockIdx.y;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= I) return;
+    const float2 g = __half22float2(*reinterpret_cast<const __half2*>(gu + (int64_t)row * 2 * I + i));
+    const __half2 u = *reinterpret_cast<const __half2*>(gu + (int64_t)row * 2 * I + I + i);
+    const __half2 a = __floats2half2_rn(g.x / (1.f + expf(-g.x)), g.y / (1.f + expf(-g.y)));
+    *reinterpret_cast<__half2*>(out + (int64_t)row * I + i) = __hmul2_rn(a, u);
+}
+
+}  // namespace kivi
+
+using namespace kivi;
+
+extern "C" int kivi_add_rmsnorm_f16(const void* x, void* residual, const void* weight, void* out,
+                                    int rows, int hidden, float eps, void* stream)
+{
+    if (!residual || !weight || !out) return KIVI_ERR_NULL;
+    if (rows < 0 || hidden <= 0 || hidden % 2 != 0 || hidden > 16384) return KIVI_ERR_SHAPE;
+    if (rows == 0) return KIVI_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x) add_rmsnorm_kernel<true><<<rows, 256, hidden * sizeof(float), st>>>((const __half*)x, (__half*)residual,
+                                                                            (const __half*)weight, (__half*)out, hidden, eps);
+    else   add_rmsnorm_kernel<false><<<rows, 256, hidden * sizeof(float), st>>>(nullptr, (__half*)residual,
+                                                                             (const __half*)weight, (__half*)out, hidden, eps);
+    return post_launch();
+}
+
+extern "C" int kivi_rope_split_f16(const void* qkv, const void* cos_table, const void* sin_table, const void* pos,
+                                   void* q, void* k, void* v, int batch, int num_heads, int num_kv_heads, void* stream)
+{
+    if (!qkv || !cos_table || !sin_table || !pos || !q || !k || !v) return KIVI_ERR_NULL;
+    if (batch <= 0 || num_heads <= 0 || num_kv_heads <= 0 || batch > 65535) return KIVI_ERR_SHAPE;
+    rope_split_kernel<<<dim3(num_heads + 2 * num_kv_heads, batch), 64, 0, (cudaStream_t)stream>>>(
+        (const __half*)qkv, (const __half*)cos_table, (const __half*)sin_table, (const long long*)pos,
+        (__half*)q, (__half*)k, (__half*)v, num_heads, num_kv_heads);
+    return post_launch();
+}
+
+extern "C" int kivi_silu_mul_f16(const void* gate_up, void* out, int rows, int intermediate, void* stream)
+{
+    if (!gate_up || !out) return KIVI_ERR_NULL;
+    if (rows <= 0 || intermediate <= 0 || intermediate % 2 != 0 || rows > 65535) return KIVI_ERR_SHAPE;
+    silu_mul_kernel<<<dim3(cdiv(intermediate / 2, 256), rows), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)gate_up, (__half*)out, intermediate);
+    return post_launch();
+}

@@ -343,11 +343,61 @@ class LlamaForCausalLM_KIVI(nn.Module):
         self._pos.fill_(n)
 
     def _step_body(self):
-        pasts = [(self.cache, i) for i in range(len(self.model.layers))]
-        h, _ = self._run_layers(self._ids, self._pos, pasts)
-        self._logits.copy_(self.lm_head(h[:, 0]).float())
+        if self._fast_ok():
+            self._step_body_fast()
+        else:
+            pasts = [(self.cache, i) for i in range(len(self.model.layers))]
+            h, _ = self._run_layers(self._ids, self._pos, pasts)
+            self._logits.copy_(self.lm_head(h[:, 0]).float())
         self.cache_advance_device()
         self._pos.add_(1)
+
+    def _fast_ok(self):
+        a = self.model.layers[0].self_attn
+        return a.head_dim == 128 and a.q_proj.bias is None and self.lm_head.weight.dtype == torch.float16
+
+    def _ensure_fast(self):
+        """Concatenated q|k|v and gate|up weights + static activation buffers for the 9-launch-per-layer step."""
+        if getattr(self, "_fast", None) is not None and self._fast.B == self.cache.batch:
+            return self._fast
+        cfg, dev, B = self.config, self.cache.device, self.cache.batch
+        H, Hkv, hid, inter = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.hidden_size, cfg.intermediate_size
+        f = SimpleNamespace(B=B)
+        f.wqkv = [torch.cat([l.self_attn.q_proj.weight, l.self_attn.k_proj.weight, l.self_attn.v_proj.weight], 0).contiguous()
+                  for l in self.model.layers]
+        f.wgu = [torch.cat([l.mlp.gate_proj.weight, l.mlp.up_proj.weight], 0).contiguous() for l in self.model.layers]
+        e = lambda *shape: torch.empty(shape, dtype=torch.float16, device=dev)  # noqa: E731
+        f.res, f.h, f.o, f.d = e(B, hid), e(B, hid), e(B, hid), e(B, hid)
+        f.qkv, f.q, f.k, f.v = e(B, (H + 2 * Hkv) * 128), e(B, H, 128), e(B, Hkv, 128), e(B, Hkv, 128)
+        f.attn, f.gu, f.act = e(B, H, 128), e(B, 2 * inter), e(B, inter)
+        f.logits16 = e(B, cfg.vocab_size)
+        self._fast = f
+        return f
+
+    def _step_body_fast(self):
+        """One decode step with 9 launches per layer: 4 cuBLAS GEMMs (q|k|v, o, gate|up, down), RoPE+split,
+        fused KIVI attention, SiLU*mul and two residual-add+RMSNorm kernels."""
+        from . import glue
+        f = self._ensure_fast()
+        cfg, cache = self.config, self.cache
+        cos_t, sin_t = self._tables(cache.device)
+        eps = cfg.rms_norm_eps
+        layers = self.model.layers
+        f.res.copy_(self.model.embed_tokens(self._ids)[:, 0])
+        glue.add_rmsnorm(None, f.res, layers[0].input_layernorm.weight, f.h, eps)
+        for i, l in enumerate(layers):
+            torch.mm(f.h, f.wqkv[i].t(), out=f.qkv)
+            glue.rope_split(f.qkv, cos_t, sin_t, self._pos, f.q, f.k, f.v)
+            cache.decode_attention(i, f.q, f.k, f.v, out=f.attn)
+            torch.mm(f.attn.view(f.B, -1), l.self_attn.o_proj.weight.t(), out=f.o)
+            glue.add_rmsnorm(f.o, f.res, l.post_attention_layernorm.weight, f.h, eps)
+            torch.mm(f.h, f.wgu[i].t(), out=f.gu)
+            glue.silu_mul(f.gu, f.act)
+            torch.mm(f.act, l.mlp.down_proj.weight.t(), out=f.d)
+            nxt = layers[i + 1].input_layernorm.weight if i + 1 < len(layers) else self.model.norm.weight
+            glue.add_rmsnorm(f.d, f.res, nxt, f.h, eps)
+        torch.mm(f.h, self.lm_head.weight.t(), out=f.logits16)
+        self._logits.copy_(f.logits16)                                       # logits.float() (:881)
 
     def cache_advance_device(self):
         from . import _lib

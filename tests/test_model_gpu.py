@@ -90,3 +90,42 @@ def test_generate_runs():
     ids = torch.randint(0, cfg.vocab_size, (3, 140), device="cuda")
     out = model.generate(ids, max_new_tokens=10)
     assert out.shape == (3, 150) and torch.equal(out[:, :140], ids)
+
+
+def test_glue_kernels_match_torch():
+    """The decode-step glue kernels reproduce the fp16 op chains of the HF Llama modules."""
+    from kivi_b200 import glue
+    from kivi_b200.llama_kivi import _rope_tables, _rotate_half
+    torch.manual_seed(0)
+    B, H, Hkv, hid, inter = 5, 4, 2, 512, 1408
+    # residual-add + RMSNorm (LlamaRMSNorm: fp32 statistics, cast, multiply by the fp16 weight)
+    x = torch.randn(B, hid, device="cuda", dtype=torch.float16)
+    res = torch.randn(B, hid, device="cuda", dtype=torch.float16)
+    w = (torch.rand(hid, device="cuda") + 0.5).half()
+    r2 = res.clone()
+    out = torch.empty_like(x)
+    glue.add_rmsnorm(x, r2, w, out, 1e-5)
+    exp_res = res + x
+    hs = exp_res.float()
+    exp = w * (hs * torch.rsqrt(hs.pow(2).mean(-1, keepdim=True) + 1e-5)).half()
+    assert torch.equal(r2, exp_res)
+    assert (out.float() - exp.float()).abs().max() <= 2e-3 * exp.float().abs().max()
+    # RoPE + split
+    qkv = torch.randn(B, (H + 2 * Hkv) * 128, device="cuda", dtype=torch.float16)
+    cos_t, sin_t = _rope_tables(128, 64, 10000.0, torch.device("cuda"))
+    pos = torch.full((B, 1), 37, dtype=torch.long, device="cuda")
+    q = torch.empty(B, H, 128, device="cuda", dtype=torch.float16)
+    k = torch.empty(B, Hkv, 128, device="cuda", dtype=torch.float16)
+    v = torch.empty_like(k)
+    glue.rope_split(qkv, cos_t, sin_t, pos, q, k, v)
+    q0, k0, v0 = qkv.view(B, H + 2 * Hkv, 128).split([H, Hkv, Hkv], dim=1)
+    c, s = cos_t[37], sin_t[37]
+    assert torch.equal(q, q0 * c + _rotate_half(q0) * s)
+    assert torch.equal(k, k0 * c + _rotate_half(k0) * s)
+    assert torch.equal(v, v0)
+    # SiLU * mul
+    gu = torch.randn(B, 2 * inter, device="cuda", dtype=torch.float16)
+    act = torch.empty(B, inter, device="cuda", dtype=torch.float16)
+    glue.silu_mul(gu, act)
+    exp = torch.nn.functional.silu(gu[:, :inter]) * gu[:, inter:]
+    assert (act.float() - exp.float()).abs().max() <= 2e-3 * exp.float().abs().max() + 1e-4
