@@ -223,12 +223,12 @@ def run_ours(args):
     ids_dev = torch.empty((B, 1), dtype=torch.long, device=dev)
 
     def step_e2e():
-        ids_dev.copy_(ids_host, non_blocking=True)
+        ids_dev.copy_(ids_host, non_blocking=True)              # H2D: this step's token ids (pinned)
         logits = model.decode_step(ids_dev)
-        full = kdist.gather_logits(logits, Bg)
-        logits_host.copy_(full[lo:hi], non_blocking=True)
+        toks, mine = kdist.greedy_next_tokens(logits, rank, ws, Bg)
+        logits_host.copy_(logits, non_blocking=True)           # D2H: the step's result (logits of this shard)
+        ids_host.copy_(mine.view(B, 1), non_blocking=True)     # D2H: sampled ids, fed back from the host next step
         torch.cuda.current_stream().synchronize()
-        ids_host.copy_(logits_host.argmax(-1, keepdim=True))   # host-side greedy pick of this shard
 
     for _ in range(W):
         step_e2e()
@@ -302,7 +302,7 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 (fp32 accumulate; 2-bit codes)", "data": "synthetic", "config": workload_config(args),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * vocab * 4,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * vocab * 4 + B * 8,
                         "ms_per_step": ms_e2e / n_e2e},
                 "gpu_launches": launches_per_step * K,
                 "gpu_launches_note": f"{launches_per_step} libkivi_b200 launches per step (32 fused decode-attention + 1 "
