@@ -174,6 +174,14 @@ int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const vo
                               const void* mask, void* out, void* dbg_logits, void* dbg_probs,
                               int64_t dbg_stride, int max_kv_len, void* stream);
 
+/* The same decode attention as kivi_decode_attention_f16, as three barrier-free launches (q.K^T into a
+ * global fp16 workspace, row softmax, p.V + cache update).  No shared-memory bound on the context
+ * length; the intermediate logits / probabilities make one round trip through L2/HBM.
+ *   workspace: fp16 [B*H, ld], ld % 8 == 0, ld >= kv_len + 1 + 8; on return it holds the probabilities. */
+int kivi_decode_attention_split_f16(const kivi_cache_t* cache, const void* q, const void* k_new, const void* v_new,
+                                    const void* mask, void* out, void* workspace, int64_t ld,
+                                    void* dbg_logits, void* dbg_probs, int64_t dbg_stride, void* stream);
+
 /* Advance `state` by one token (the bookkeeping of :343-356, :386-399); once per step, all layers. */
 int kivi_cache_advance(const kivi_cache_t* cache, void* stream);
 

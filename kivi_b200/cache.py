@@ -34,6 +34,7 @@ def _bind():
     _lib.bind("kivi_cache_sizes", i32, [i32] * 7 + [ctypes.POINTER(i64)])
     _lib.bind("kivi_cache_prefill_f16", i32, [P, vp, vp, i32, vp])
     _lib.bind("kivi_decode_attention_f16", i32, [P, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp])
+    _lib.bind("kivi_decode_attention_split_f16", i32, [P, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp])
     _lib.bind("kivi_cache_advance", i32, [P, vp])
     _lib.bind("kivi_cache_export_f16", i32, [P, i32, i32, i32, i32, i32] + [vp] * 9)
     _BOUND = True
@@ -68,6 +69,8 @@ class KiviCache:
                               *[b.data_ptr() for b in bufs], self.state.data_ptr())
             self._bufs.append(bufs)
             self._structs.append(st)
+        self.mode = "fused"        # "fused": one launch per layer; "split": q.K^T / softmax / p.V launches (any context length)
+        self._ws = None
         # host mirror of `state` (its evolution is deterministic)
         self.tk = self.r = self.tv = self.L = self.vhead = self.kv_len = 0
 
@@ -111,7 +114,8 @@ class KiviCache:
 
     def decode_attention(self, layer: int, q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor,
                          mask: torch.Tensor | None = None, out: torch.Tensor | None = None,
-                         dbg_logits: torch.Tensor | None = None, dbg_probs: torch.Tensor | None = None):
+                         dbg_logits: torch.Tensor | None = None, dbg_probs: torch.Tensor | None = None,
+                         mode: str | None = None):
         """One fused launch: attention of q [B,H,128] over the cache + k_new/v_new [B,Hkv,128], then the
         cache update for this layer.  Call advance() once after the last layer of the step."""
         _lib.require_cuda(q, k_new, v_new)
@@ -130,6 +134,19 @@ class KiviCache:
             if d is not None:
                 assert d.dtype == torch.float16 and d.is_contiguous() and d.shape[:2] == (self.batch, self.num_heads)
                 stride = d.shape[-1]
+        mode = mode or self.mode
+        if mode == "split":
+            if self._ws is None:
+                ld = (self.max_tokens + 16 + 7) // 8 * 8
+                self._ws = torch.zeros((self.batch * self.num_heads, ld), dtype=torch.float16, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().kivi_decode_attention_split_f16(
+                    ctypes.byref(self._structs[layer]), q.data_ptr(), k_new.data_ptr(), v_new.data_ptr(),
+                    mask.data_ptr() if mask is not None else None, out.data_ptr(), self._ws.data_ptr(), self._ws.shape[1],
+                    dbg_logits.data_ptr() if dbg_logits is not None else None,
+                    dbg_probs.data_ptr() if dbg_probs is not None else None, stride,
+                    _lib.stream_ptr(self.device)), "kivi_decode_attention_split_f16")
+            return out
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().kivi_decode_attention_f16(
                 ctypes.byref(self._structs[layer]), q.data_ptr(), k_new.data_ptr(), v_new.data_ptr(),

@@ -210,17 +210,18 @@ __device__ __forceinline__ void kq_quarter(const uint8_t* st, int qt, const floa
 }
 
 // cache data movement of one unit (models/llama_kivi.py:343-356, :386-399); cold path, kept out of line
+// executed by a team of `tsize` threads (multiple of 32); `tid` = index within the team
 template <int KB, int VB>
-__device__ __noinline__ void commit_unit(const DecodeParams& p, const Sched& s, int u)
+__device__ __noinline__ void commit_unit(const DecodeParams& p, const Sched& s, int u, int tid, int tsize)
 {
     const CacheDesc& c = p.c;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp = tid >> 5, lane = tid & 31;
     const int g = c.g;
     // V: v_new joins the ring; if the window would exceed R, its oldest token is quantised
     if (tid < kD / 8)
         reinterpret_cast<uint4*>(c.v_res + ((int64_t)u * c.v_res_cap + (s.vhead + s.L) % c.v_res_cap) * kD)[tid] =
             __ldg(reinterpret_cast<const uint4*>(p.v_new + (int64_t)u * kD) + tid);
-    if (s.L + 1 > c.R && warp == 1) {
+    if (s.L + 1 > c.R && warp == (tsize > 32 ? 1 : 0)) {
         constexpr int FPI = 32 / VB, WPT = kD / FPI;
         const float maxq = (float)((1 << VB) - 1);
         const __half* src = c.v_res + ((int64_t)u * c.v_res_cap + s.vhead) * kD;
@@ -257,9 +258,9 @@ __device__ __noinline__ void commit_unit(const DecodeParams& p, const Sched& s, 
     }
     // K: k_new joins the window, or completes it -> quantise the R tokens per channel
     if (s.r + 1 < c.R) {
-        if (tid >= 64 && tid < 64 + kD / 8)
-            reinterpret_cast<uint4*>(c.k_res + ((int64_t)u * c.R + s.r) * kD)[tid - 64] =
-                __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (tid - 64));
+        if (tid >= 16 && tid < 16 + kD / 8)
+            reinterpret_cast<uint4*>(c.k_res + ((int64_t)u * c.R + s.r) * kD)[tid - 16] =
+                __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (tid - 16));
     } else {
         constexpr int FPI = 32 / KB;
         constexpr int cbk = 4 * KB;
@@ -267,7 +268,7 @@ __device__ __noinline__ void commit_unit(const DecodeParams& p, const Sched& s, 
         uint8_t* ubase = c.k_store + (int64_t)u * k_unit_bytes(c.k_cap_blocks, KB, g);
         const __half* win = c.k_res + (int64_t)u * c.R * kD;
         const __half* knew = p.k_new + (int64_t)u * kD;
-        for (int w = tid; w < kD * (c.R / g); w += kThreads) {
+        for (int w = tid; w < kD * (c.R / g); w += tsize) {
             const int d = w % kD, grp = w / kD;
             auto tokval = [&](int t) -> float {
                 return __half2float(t < c.R - 1 ? win[(int64_t)t * kD + d] : knew[d]);
@@ -615,7 +616,7 @@ decode_attention_kernel(const DecodeParams p)
             if (s.tv > 0) o = __hadd_rn(__float2half_rn(q_sum), o);                     // :382-384
             p.out[(int64_t)(uq0 + h) * kD + d] = o;
         }
-        if (hc == 0) commit_unit<KB, VB>(p, s, u);
+        if (hc == 0) commit_unit<KB, VB>(p, s, u, tid, kThreads);
         __syncthreads();                                            // qsp / lg / red are reused by the next unit
     }
 }

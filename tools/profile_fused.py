@@ -17,6 +17,7 @@ ap.add_argument("--bits", type=int, default=2)
 ap.add_argument("--g", type=int, default=32)
 ap.add_argument("--R", type=int, default=128)
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--mode", default="fused")
 a = ap.parse_args()
 gen = torch.Generator(device="cuda").manual_seed(0)
 cache = KiviCache(1, a.B, a.H, a.Hkv, 128, a.bits, a.bits, a.g, a.R, max_tokens=a.n + 256)
@@ -29,6 +30,6 @@ kn = torch.randn((a.B, a.Hkv, 128), generator=gen, device="cuda", dtype=torch.fl
 vn = torch.randn((a.B, a.Hkv, 128), generator=gen, device="cuda", dtype=torch.float16)
 out = torch.empty_like(q)
 for _ in range(a.iters):
-    cache.decode_attention(0, q, kn, vn, out=out)
+    cache.decode_attention(0, q, kn, vn, out=out, mode=a.mode)
 torch.cuda.synchronize()
 print("state", cache.tk, cache.r, cache.tv, cache.L)
