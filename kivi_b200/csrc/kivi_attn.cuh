@@ -110,26 +110,25 @@ __device__ __forceinline__ void mma_chunk(const uint8_t* codes, const uint4 meta
     #pragma unroll
     for (int r = 0; r < 4; ++r) { const float2 f = __half22float2(mh[r]); sf[r] = f.x; zf[r] = f.y; }
     uint32_t b0[G], b1[G];
+    // branch-free column select: part 0 -> hi = fp16(a); part 1 -> lo = fp16((a - hi) * 2^11)
+    const float k1 = part ? 1.f : 0.f, k2 = part ? kLoScale : 1.f;
     #pragma unroll
     for (int h = 0; h < G; ++h) {
         float a[4];
         #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            a[r] = col_valid ? x[h][r] * sf[r] : 0.f;
-            Z[h] = fmaf(col_valid ? x[h][r] : 0.f, zf[r], Z[h]);
+            const float xv = col_valid ? x[h][r] : 0.f;
+            a[r] = xv * sf[r];
+            Z[h] = fmaf(xv, zf[r], Z[h]);
         }
-        const __half2 h01 = __floats2half2_rn(a[0], a[1]), h23 = __floats2half2_rn(a[2], a[3]);
-        if (part) {
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            b0[h] = pack_h2((a[0] - f01.x) * kLoScale, (a[1] - f01.y) * kLoScale);
-            b1[h] = pack_h2((a[2] - f23.x) * kLoScale, (a[3] - f23.y) * kLoScale);
-        } else {
-            b0[h] = *reinterpret_cast<const uint32_t*>(&h01);
-            b1[h] = *reinterpret_cast<const uint32_t*>(&h23);
-        }
+        const float2 f01 = __half22float2(__floats2half2_rn(a[0], a[1]));
+        const float2 f23 = __half22float2(__floats2half2_rn(a[2], a[3]));
+        b0[h] = pack_h2(fmaf(-f01.x, k1, a[0]) * k2, fmaf(-f01.y, k1, a[1]) * k2);
+        b1[h] = pack_h2(fmaf(-f23.x, k1, a[2]) * k2, fmaf(-f23.y, k1, a[3]) * k2);
     }
     // ---- A fragments: unpack (LOP3 + HADD2 per pair of codes) and multiply
-    constexpr uint32_t kMagic = 0x64006400u;                     // fp16 1024.0 in both halves
+    uint32_t magic;                                              // fp16 1024.0 in both halves, kept in a register
+    asm volatile("mov.b32 %0, 0x64006400;" : "=r"(magic));
     constexpr uint32_t kField = ((1u << BITS) - 1u) * 0x00010001u;
     const __half2 k1024 = __float2half2_rn(1024.f);
     #pragma unroll
@@ -145,7 +144,8 @@ __device__ __forceinline__ void mma_chunk(const uint8_t* codes, const uint4 meta
             #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const uint32_t src = j < L::kInPlace ? w[r] : ws[r];
-                const uint32_t m = (src & (kField << (BITS * L::pos(j)))) | kMagic;
+                uint32_t m;                                      // (src & mask) | magic in ONE LOP3 (magic in a register)
+                asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(m) : "r"(src), "r"(kField << (BITS * L::pos(j))), "r"(magic));
                 const __half2 v = __hsub2(*reinterpret_cast<const __half2*>(&m), k1024);
                 a[r] = *reinterpret_cast<const uint32_t*>(&v);
             }
