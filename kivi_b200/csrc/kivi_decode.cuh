@@ -1,28 +1,18 @@
-// kivi_decode.cuh -- KIVI cache layout in HBM (v2, tensor-core friendly) + mbarrier / bulk-copy (TMA)
-// PTX helpers (sm_100a).
+// kivi_decode.cuh -- KIVI cache layout in HBM + mbarrier / bulk-copy (TMA) PTX helpers (sm_100a).
 //
-// Every packed store is a sequence of 128 x 128 BLOCKS "inner x outer":
-//     K store: inner = channel d (the reduction index of q.K^T), outer = token   -> one block = 128 tokens
-//     V store: inner = token t  (the reduction index of p.V),   outer = channel  -> one block = 128 tokens
-// Quantisation groups run along the OUTER dim (g tokens per channel for K, g channels per token for V --
-// exactly the reference's per-channel K / per-token V scheme), so a block is the same object for both.
+// Cache layout (one layer; U = B * Hkv units, D = 128 channels, cell = 32 consecutive elements):
 //
-//   block = [ codes: 8 chunks x kChunkBytes ][ meta: 8 chunks x (128/g) groups x 4 x 4 half2(scale, zero) ]
-//   chunk c = inner indices 16c .. 16c+15.  Its codes are stored as the A-operand fragments of
-//   mma.sync.m16n8k16 (row = outer, col = inner), so that a lane's 128-bit shared-memory load yields its four
-//   A registers for F = 16/bits consecutive MMAs at once:
-//       word(lane = 4*g8 + t, r), r = 0..3:   pair p = t + 4*(r >> 1)  (inner 2t + 8*(r>>1) + {0, 1}),
-//                                             row  = g8 + 8*(r & 1)
-//       low  16 bits: field j (bits [bits*j, bits*j + bits)) = code[inner 2*(p%4) + 8*(p/4)    ][outer 16*j + row]
-//       high 16 bits: field j                                = code[inner 2*(p%4) + 8*(p/4) + 1][outer 16*j + row]
-//   (a "slab" = the 16*F outer rows covered by one word set: 128 rows at 2 bits, 64 rows at 4 bits.)
-//   A code is turned into an exact fp16 by OR-ing the fp16 bit pattern of 1024 around the in-place field
-//   (one LOP3 per PAIR of codes) and subtracting 1024 (one HADD2 per pair): value = code * (2^bits)^pos.
-//   meta entry (c, G, t, r) = (scale, zero) of inner index 16c + 2t + (r & 1) + 8*(r >> 1), outer group G:
-//   the four entries a lane needs for its B fragment are one 128-bit load.
-//
-//   K window [U][R][128] fp16            V window [U][R+1][128] fp16 ring buffer (head = state.vhead)
-//   state    int32[8] on the device, shared by the layers of a model: {tk, r, tv, L, vhead, kv_len}
+//   K store  [U][k_cap_blocks][4 quarters][QB bytes]    block = 128 tokens, per-channel quantised
+//            quarter qt holds channels d in [32*qt, 32*qt+32):
+//              codes [32 rows][4 cells][cbk bytes]        cbk = 4*k_bits (cell of 32 TOKENS of channel d)
+//              meta  [32 rows][128/g][half2(scale, zero)]
+//            -> a (block, quarter) is ONE contiguous, 16-B aligned run of QB bytes = one bulk copy.
+//   V store  codes [U][v_cap][4 cells][cbv bytes]         cbv = 4*v_bits (cell of 32 CHANNELS of token t)
+//            meta  [U][v_cap][128/g][half2(scale, zero)]  -> a run of tokens = two bulk copies.
+//   K residual [U][R][128] fp16           (tokens tk .. tk+r-1, newest last)
+//   V residual [U][v_res_cap][128] fp16   ring buffer, head = state.vhead, L valid tokens
+//   state    int32[8] on the device, shared by all layers of a model (every layer sees the same
+//            lengths): {tk, r, tv, L, vhead, kv_len, 0, 0}
 //
 // Policy restated from models/llama_kivi.py:343-356 (K: the fp16 window is quantised per channel in
 // groups of g tokens as soon as it holds R tokens) and :386-399 (V: the window holds the newest R
@@ -33,13 +23,15 @@
 namespace kivi {
 
 constexpr int kD = 128;            // head_dim of every model the reference ships (Llama / Mistral)
-constexpr int kBlockTokens = 128;  // tokens per block (K: outer rows, V: inner rows)
+constexpr int kBlockTokens = 128;  // K store block
+constexpr int kCell = 32;
 
 struct CacheDesc {
     int B, Hkv, H, k_bits, v_bits, g, R;
-    int k_cap_blocks, v_cap_blocks, v_res_cap;
+    int k_cap_blocks, v_cap, v_res_cap;
     uint8_t* k_store;
-    uint8_t* v_store;
+    uint8_t* v_codes;
+    uint8_t* v_meta;
     __half* k_res;
     __half* v_res;
     int* state;
@@ -47,42 +39,21 @@ struct CacheDesc {
 
 enum { ST_TK = 0, ST_R = 1, ST_TV = 2, ST_L = 3, ST_VHEAD = 4, ST_KVLEN = 5 };
 
-template <int BITS>
-struct Lay {
-    static constexpr int F = 16 / BITS;                  // fields per 16-bit half = MMAs per slab
-    static constexpr int kSlabRows = 16 * F;             // outer rows per slab (128 / 64)
-    static constexpr int kSlabs = 128 / kSlabRows;       // slabs per block (1 / 2)
-    static constexpr int kChunkBytes = 512 * kSlabs;     // 128 words per slab
-    static constexpr int kCodeBytes = 8 * kChunkBytes;   // 4096 / 8192
-    // position (in units of `bits`) of field j inside the 16-bit half after the optional shift
-    static constexpr int kInPlace = BITS == 2 ? 5 : 2;   // fields 0 .. kInPlace-1 are used in place (value < 1024)
-    __host__ __device__ static constexpr int pos(int j) { return j < kInPlace ? j : j - kInPlace; }
-    static constexpr int kShift = BITS * kInPlace;       // 10 / 8: brings the remaining fields to positions 0..
-};
-
-__host__ __device__ inline int lay_code_bytes(int bits) { return bits == 2 ? 4096 : 8192; }
-__host__ __device__ inline int lay_meta_bytes(int g) { return 8 * (128 / g) * 16 * 4; }
-__host__ __device__ inline int lay_block_bytes(int bits, int g) { return lay_code_bytes(bits) + lay_meta_bytes(g); }
-
-// byte offset (inside a block) of the word holding element (inner i, outer o), and its bit position
-__host__ __device__ inline int lay_word_off(int bits, int i, int o) {
-    const int F = 16 / bits, slab_rows = 16 * F, slabs = 128 / slab_rows;
-    const int c = i >> 4, ii = i & 15;
-    const int p = ((ii & 7) >> 1) + 4 * (ii >> 3);
-    const int sl = o / slab_rows, row = o % 16;
-    const int lane = (row & 7) * 4 + (p & 3), r = (p >> 2) * 2 + (row >> 3);
-    return ((c * slabs + sl) * 128 + lane * 4 + r) * 4;
+__host__ __device__ inline int k_cell_bytes(int bits) { return 4 * bits; }
+constexpr int kQRows = 32;         // channels per K quarter
+__host__ __device__ inline int k_q_code_bytes(int bits) { return kQRows * 4 * k_cell_bytes(bits); }
+__host__ __device__ inline int k_q_meta_bytes(int g) { return kQRows * (kBlockTokens / g) * 4; }
+__host__ __device__ inline int k_q_bytes(int bits, int g) { return k_q_code_bytes(bits) + k_q_meta_bytes(g); }
+// byte offset of the (block, channel d) row inside a unit's K store, and of its meta row
+__host__ __device__ inline int64_t k_row_off(int blk, int d, int bits, int g) {
+    return ((int64_t)blk * 4 + d / kQRows) * k_q_bytes(bits, g) + (d % kQRows) * (4 * k_cell_bytes(bits));
 }
-__host__ __device__ inline int lay_bit_pos(int bits, int i, int o) {
-    const int F = 16 / bits, slab_rows = 16 * F;
-    return 16 * (i & 1) + bits * ((o % slab_rows) >> 4);
+__host__ __device__ inline int64_t k_meta_off(int blk, int d, int bits, int g) {
+    return ((int64_t)blk * 4 + d / kQRows) * k_q_bytes(bits, g) + k_q_code_bytes(bits) + (d % kQRows) * ((kBlockTokens / g) * 4);
 }
-// byte offset (inside a block) of the half2 (scale, zero) of (inner i, outer group G)
-__host__ __device__ inline int lay_meta_off(int bits, int g, int i, int G) {
-    const int c = i >> 4, ii = i & 15;
-    const int t = (ii & 7) >> 1, r = (ii & 1) + 2 * (ii >> 3);
-    return lay_code_bytes(bits) + ((((c * (128 / g)) + G) * 4 + t) * 4 + r) * 4;
-}
+__host__ __device__ inline int64_t k_unit_bytes(int cap_blocks, int bits, int g) { return (int64_t)cap_blocks * 4 * k_q_bytes(bits, g); }
+__host__ __device__ inline int v_tok_code_bytes(int bits) { return 4 * 4 * bits; }           // 128 channels
+__host__ __device__ inline int v_tok_meta_bytes(int g) { return (kD / g) * 4; }
 
 // ---- PTX helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,14 +99,6 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col)      (SASS: HMMA.16816.F32)
-__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                          uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 }  // namespace kivi

@@ -1,0 +1,6 @@
+// instantiation of the fused and split decode kernels for k_bits = 2, v_bits = 2 (all G, all group sizes)
+#include "kivi_decode_split.cuh"
+namespace kivi {
+int decode_k2v2(DecodeParams& p, int G, int max_kv_len, cudaStream_t st) { return dispatch_decode<2, 2>(p, G, max_kv_len, st); }
+int decode_split_k2v2(SplitParams& sp, int G, cudaStream_t st) { return dispatch_decode_split<2, 2>(sp, G, st); }
+}

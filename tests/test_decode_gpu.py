@@ -34,9 +34,11 @@ def _tuple_equal(got, exp):
             np.testing.assert_array_equal(a, b, err_msg=f"tuple[{i}]")
 
 
-def _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=1024, n_layers=1):
+def _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=1024, n_layers=1, mode="fused"):
     from kivi_b200.cache import KiviCache
-    return KiviCache(n_layers, B, H, Hkv, 128, kb, vb, g, R, max_tokens)
+    c = KiviCache(n_layers, B, H, Hkv, 128, kb, vb, g, R, max_tokens)
+    c.mode = mode
+    return c
 
 
 @pytest.mark.parametrize("n", [1, 5, 128, 200, 333, 640])
@@ -129,10 +131,11 @@ DECODE_CASES = [  # B, H, Hkv, kb, vb, g, R, n_prefill, steps
 ]
 
 
+@pytest.mark.parametrize("mode", ["fused", "split"])
 @pytest.mark.parametrize("B,H,Hkv,kb,vb,g,R,n0,steps", DECODE_CASES)
-def test_decode_steps_match_oracle(B, H, Hkv, kb, vb, g, R, n0, steps):
+def test_decode_steps_match_oracle(B, H, Hkv, kb, vb, g, R, n0, steps, mode):
     rng = np.random.default_rng(n0 * 13 + H + R)
-    cache = _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=512)
+    cache = _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=512, mode=mode)
     if n0 > 0:
         k = rng.standard_normal((B, Hkv, n0, 128)).astype(np.float16)
         v = rng.standard_normal((B, Hkv, n0, 128)).astype(np.float16)
@@ -178,11 +181,12 @@ def _oracle_step(st, q, k_new, v_new, g, kb, vb, R, mask=None):
     return ref.decode_step(st, q, k_new, v_new, g, kb, vb, R, mask)
 
 
-def test_decode_with_mask():
+@pytest.mark.parametrize("mode", ["fused", "split"])
+def test_decode_with_mask(mode):
     """Additive mask + max with finfo.min (models/llama_kivi.py:364-372), e.g. left padding."""
     rng = np.random.default_rng(4)
     B, H, Hkv, kb, vb, g, R, n0 = 2, 2, 2, 2, 2, 32, 128, 200
-    cache = _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=512)
+    cache = _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=512, mode=mode)
     k = rng.standard_normal((B, Hkv, n0, 128)).astype(np.float16)
     v = rng.standard_normal((B, Hkv, n0, 128)).astype(np.float16)
     cache.prefill(0, torch.from_numpy(k).cuda(), torch.from_numpy(v).cuda())
@@ -230,7 +234,8 @@ def test_multi_layer_shared_state():
         _tuple_equal(cache.export(l), sts[l])
 
 
-def test_full_size_consistency():
+@pytest.mark.parametrize("mode", ["fused", "split"])
+def test_full_size_consistency(mode):
     """BASELINE cfg 2 layer shape (B32, H32, T = 4096, K2V2 g32 R128): too big for the CPU oracle end to
     end, so (1) a slab of units is checked stage-by-stage against the oracle, (2) the fused kernel must
     agree with the library's own generic-layout kernels run on the exported cache for ALL units
@@ -238,7 +243,7 @@ def test_full_size_consistency():
     from kivi_b200 import matmul
     gen = torch.Generator(device="cuda").manual_seed(3)
     B, H, Hkv, g, R, n0 = 32, 32, 32, 32, 128, 4095
-    cache = _mk_cache(B, H, Hkv, 2, 2, g, R, max_tokens=4352)
+    cache = _mk_cache(B, H, Hkv, 2, 2, g, R, max_tokens=4352, mode=mode)
     k = torch.randn((B, Hkv, n0, 128), generator=gen, device="cuda", dtype=torch.float16)
     v = torch.randn((B, Hkv, n0, 128), generator=gen, device="cuda", dtype=torch.float16)
     cache.prefill(0, k, v)
