@@ -69,7 +69,9 @@ class KiviCache:
                               *[b.data_ptr() for b in bufs], self.state.data_ptr())
             self._bufs.append(bufs)
             self._structs.append(st)
-        self.mode = "fused"        # "fused": one launch per layer; "split": q.K^T / softmax / p.V launches (any context length)
+        # "fused": one launch per layer; "split": q.K^T / softmax / p.V launches (any context length)
+        import os
+        self.mode = os.environ.get("KIVI_ATTN_MODE", "auto")   # auto: fused while its [G][T] fp16 row fits in shared memory
         self._ws = None
         # host mirror of `state` (its evolution is deterministic)
         self.tk = self.r = self.tv = self.L = self.vhead = self.kv_len = 0
@@ -135,6 +137,14 @@ class KiviCache:
                 assert d.dtype == torch.float16 and d.is_contiguous() and d.shape[:2] == (self.batch, self.num_heads)
                 stride = d.shape[-1]
         mode = mode or self.mode
+        if mode == "auto":
+            try:
+                return self.decode_attention(layer, q, k_new, v_new, mask=mask, out=out, dbg_logits=dbg_logits,
+                                             dbg_probs=dbg_probs, mode="fused")
+            except _lib.KiviError as e:
+                if e.code != -8:                                   # KIVI_ERR_CAPACITY: context too long for the fused kernel
+                    raise
+                self.mode = mode = "split"
         if mode == "split":
             if self._ws is None:
                 ld = (self.max_tokens + 16 + 7) // 8 * 8

@@ -1,5 +1,6 @@
 // kivi_decode.cu -- C-ABI entry of the fused decode attention; the kernel lives in kivi_decode_impl.cuh and is
 // instantiated per (k_bits, v_bits) pair in kivi_decode_k{2,4}v{2,4}.cu (compiled in parallel).
+#include <cstdlib>
 #include "kivi_decode_split.cuh"
 
 namespace kivi {
@@ -28,7 +29,8 @@ extern "C" int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* 
     p.q = (const __half*)q; p.k_new = (const __half*)k_new; p.v_new = (const __half*)v_new; p.mask = (const __half*)mask;
     p.out = (__half*)out; p.dbg_logits = (__half*)dbg_logits; p.dbg_probs = (__half*)dbg_probs; p.dbg_stride = dbg_stride;
     const int ratio = p.c.H / p.c.Hkv;
-    const int G = ratio % 4 == 0 ? 4 : (ratio % 2 == 0 ? 2 : 1);
+    int G = ratio % 4 == 0 ? 4 : (ratio % 2 == 0 ? 2 : 1);
+    if (const char* e = getenv("KIVI_GQA_G")) { const int g = atoi(e); if ((g == 1 || g == 2 || g == 4) && ratio % g == 0) G = g; }
     p.hchunks = ratio / G;
     p.n_units = p.c.B * p.c.Hkv * p.hchunks;
     cudaStream_t st = (cudaStream_t)stream;
@@ -49,6 +51,7 @@ extern "C" int kivi_decode_attention_split_f16(const kivi_cache_t* cache, const 
     if (rc) return rc;
     if (!q || !k_new || !v_new || !out || !workspace) return KIVI_ERR_NULL;
     if (ld <= 0 || ld % 8 != 0) return KIVI_ERR_ALIGN;
+    if (ld > 40960) return KIVI_ERR_CAPACITY;                 // softmax_rows_kernel keeps a row in registers
     if (reinterpret_cast<uintptr_t>(workspace) % 16 != 0) return KIVI_ERR_ALIGN;
     p.q = (const __half*)q; p.k_new = (const __half*)k_new; p.v_new = (const __half*)v_new; p.mask = (const __half*)mask;
     p.out = (__half*)out; p.dbg_logits = (__half*)dbg_logits; p.dbg_probs = (__half*)dbg_probs; p.dbg_stride = dbg_stride;

@@ -225,24 +225,49 @@ static __global__ void __launch_bounds__(256)
 softmax_rows_kernel(__half* __restrict__ ws, long long ld, const int* __restrict__ state, const __half* __restrict__ mask,
                     int H, __half* __restrict__ dbg_logits, __half* __restrict__ dbg_probs, long long dbg_stride)
 {
+    // the row is held in registers between the passes: 8 halfs (one 128-bit access) per thread per 2048 tokens
+    constexpr int kMaxIter = 20;                                   // rows of up to 40960 tokens are held in registers
     __shared__ float stats[16];
     const int T = state[ST_TK] + state[ST_R] + 1;
     const int rowi = blockIdx.x, b = rowi / H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    __half* row = ws + (int64_t)rowi * ld;
+    __half* row = ws + (int64_t)rowi * ld;                          // 16-B aligned (ld % 8 == 0)
+    const int nvec = (T + 7) / 8;
+    uint4 v[kMaxIter];
     float ml = -INFINITY;
-    for (int t = tid; t < T; t += 256) {
-        __half v = row[t];
-        if (mask) {
-            v = __hadd_rn(v, mask[(int64_t)b * T + t]);
-            if (__half2float(v) < -65504.f) v = __float2half_rn(-65504.f);
-            row[t] = v;
+    #pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int i = tid + it * 256;
+        if (i < nvec) {
+            uint4 u = *reinterpret_cast<const uint4*>(row + i * 8);
+            __half* h = reinterpret_cast<__half*>(&u);
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int t = i * 8 + e;
+                if (t < T) {
+                    if (mask) {
+                        h[e] = __hadd_rn(h[e], mask[(int64_t)b * T + t]);                   // llama_kivi.py:369
+                        if (__half2float(h[e]) < -65504.f) h[e] = __float2half_rn(-65504.f);  // :370-372
+                    }
+                    if (dbg_logits) dbg_logits[(int64_t)rowi * dbg_stride + t] = h[e];
+                    ml = fmaxf(ml, __half2float(h[e]));
+                } else {
+                    h[e] = __float2half_rn(-65504.f);               // padding of the last vector: exp -> 0
+                }
+            }
+            v[it] = u;
         }
-        if (dbg_logits) dbg_logits[(int64_t)rowi * dbg_stride + t] = v;
-        ml = fmaxf(ml, __half2float(v));
     }
     float sl = 0.f;
-    for (int t = tid; t < T; t += 256) sl += __expf(__half2float(row[t]) - ml);
+    #pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int i = tid + it * 256;
+        if (i < nvec) {
+            const __half* h = reinterpret_cast<const __half*>(&v[it]);
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) if (i * 8 + e < T) sl += __expf(__half2float(h[e]) - ml);
+        }
+    }
     #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         const float mo = __shfl_xor_sync(0xffffffffu, ml, o), so = __shfl_xor_sync(0xffffffffu, sl, o);
@@ -258,10 +283,20 @@ softmax_rows_kernel(__half* __restrict__ ws, long long ld, const int* __restrict
     float S = 0.f;
     #pragma unroll
     for (int w = 0; w < 8; ++w) S += stats[w] == -INFINITY ? 0.f : stats[8 + w] * __expf(stats[w] - M);
-    for (int t = tid; t < T; t += 256) {
-        const __half pr = __float2half_rn(__fdiv_rn(__expf(__half2float(row[t]) - M), S));
-        row[t] = pr;
-        if (dbg_probs) dbg_probs[(int64_t)rowi * dbg_stride + t] = pr;
+    #pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int i = tid + it * 256;
+        if (i < nvec) {
+            uint4 u = v[it];
+            __half* h = reinterpret_cast<__half*>(&u);
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int t = i * 8 + e;
+                h[e] = __float2half_rn(__fdiv_rn(__expf(__half2float(h[e]) - M), S));       // :375
+                if (dbg_probs && t < T) dbg_probs[(int64_t)rowi * dbg_stride + t] = h[e];
+            }
+            *reinterpret_cast<uint4*>(row + i * 8) = u;             // the <= 7 halfs past T stay inside the row (ld >= T + 8)
+        }
     }
 }
 

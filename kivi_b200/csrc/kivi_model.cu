@@ -8,36 +8,60 @@ namespace kivi {
 
 // residual (fp16, in/out) += x;  out = weight * fp16( residual * rsqrt(mean(residual^2) + eps) )
 // (LlamaRMSNorm.forward: fp32 statistics, cast to fp16, then multiply by the fp16 weight)
+// One CTA per row, every thread keeps its 8-element slices in registers between the two passes.
 template <bool ADD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 add_rmsnorm_kernel(const __half* __restrict__ x, __half* __restrict__ residual, const __half* __restrict__ w,
                    __half* __restrict__ out, int hidden, float eps)
 {
-    extern __shared__ float buf[];                       // hidden floats
-    __shared__ float red[8];
+    constexpr int kMaxIter = 4;                          // hidden <= 4 * 512 * 8 = 16384
+    __shared__ float red[16];
     const int row = blockIdx.x;
     __half* r = residual + (int64_t)row * hidden;
+    const int nvec = hidden / 8;
+    uint4 v[kMaxIter];
     float ss = 0.f;
-    for (int i = threadIdx.x * 2; i < hidden; i += blockDim.x * 2) {
-        __half2 v = *reinterpret_cast<const __half2*>(r + i);
-        if (ADD) {
-            v = __hadd2_rn(v, *reinterpret_cast<const __half2*>(x + (int64_t)row * hidden + i));
-            *reinterpret_cast<__half2*>(r + i) = v;
+    #pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int i = threadIdx.x + it * 512;
+        if (i < nvec) {
+            uint4 u = *reinterpret_cast<const uint4*>(r + i * 8);
+            __half2* h = reinterpret_cast<__half2*>(&u);
+            if (ADD) {
+                const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)row * hidden) + i);
+                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __hadd2_rn(h[e], xh[e]);
+                *reinterpret_cast<uint4*>(r + i * 8) = u;
+            }
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
+            v[it] = u;
         }
-        const float2 f = __half22float2(v);
-        buf[i] = f.x; buf[i + 1] = f.y;
-        ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
     }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
     #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i];
+    for (int i = 0; i < 16; ++i) tot += red[i];
     const float rs = rsqrtf(tot / (float)hidden + eps);
-    for (int i = threadIdx.x * 2; i < hidden; i += blockDim.x * 2) {
-        const __half2 n = __floats2half2_rn(buf[i] * rs, buf[i + 1] * rs);
-        *reinterpret_cast<__half2*>(out + (int64_t)row * hidden + i) = __hmul2_rn(*reinterpret_cast<const __half2*>(w + i), n);
+    #pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int i = threadIdx.x + it * 512;
+        if (i < nvec) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[it]);
+            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + i);
+            const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                oh[e] = __hmul2_rn(wh[e], __floats2half2_rn(f.x * rs, f.y * rs));
+            }
+            *reinterpret_cast<uint4*>(out + (int64_t)row * hidden + i * 8) = o;
+        }
     }
 }
 
@@ -86,12 +110,12 @@ extern "C" int kivi_add_rmsnorm_f16(const void* x, void* residual, const void* w
                                     int rows, int hidden, float eps, void* stream)
 {
     if (!residual || !weight || !out) return KIVI_ERR_NULL;
-    if (rows < 0 || hidden <= 0 || hidden % 2 != 0 || hidden > 16384) return KIVI_ERR_SHAPE;
+    if (rows < 0 || hidden <= 0 || hidden % 8 != 0 || hidden > 16384) return KIVI_ERR_SHAPE;
     if (rows == 0) return KIVI_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (x) add_rmsnorm_kernel<true><<<rows, 256, hidden * sizeof(float), st>>>((const __half*)x, (__half*)residual,
+    if (x) add_rmsnorm_kernel<true><<<rows, 512, 0, st>>>((const __half*)x, (__half*)residual,
                                                                             (const __half*)weight, (__half*)out, hidden, eps);
-    else   add_rmsnorm_kernel<false><<<rows, 256, hidden * sizeof(float), st>>>(nullptr, (__half*)residual,
+    else   add_rmsnorm_kernel<false><<<rows, 512, 0, st>>>(nullptr, (__half*)residual,
                                                                              (const __half*)weight, (__half*)out, hidden, eps);
     return post_launch();
 }
