@@ -41,47 +41,70 @@ UNIT = "tokens/s"
 # clocks sampling (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region: NVML polled from a thread every 5 ms (a 16-step
+    timed region lasts ~0.1 s, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, gpu_index: int = 0):
-        self.rows, self.proc, self.gpu_index = [], None, gpu_index
+        self.gpu_index, self.sm, self.mask, self.power = gpu_index, [], 0, []
+        self.h, self.nv, self.stop_flag, self.th, self.mx = None, None, False, None, None
+
+    def _handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        self.nv = pynvml
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu_index])
+                except Exception:
+                    pass
+            return pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.h = self._handle()
+            self.mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.h = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
+        if self.h is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            if self.sm:
+                return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.mx,
+                        "reasons": sorted(n for n, bit in self.REASONS if self.mask & bit),
+                        "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm), "source": "nvml 5 ms poll"}
+        try:    # fallback: one nvidia-smi query right after the timed region
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                  "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1,
+                    "source": "nvidia-smi after the timed region (NVML unavailable)"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx = float(r[2])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -145,7 +145,8 @@ def test_pack_full_size_properties(bits, g, shape):
     assert torch.equal(scale, exp_scale)
     deq = new_pack._unpack_dequant_lastdim(code, scale, mn, g, bits)
     err = (deq.float() - x.float()).abs().view(xg.shape)
-    bound = scale.float().unsqueeze(-1) * 0.5 + (x.float().abs().view(xg.shape) + 1) * 2e-3
+    # t2 = fp16((x - mn) / scale) is rounded to fp16 before rint(): up to 2^-7 code units near 15 (4-bit)
+    bound = scale.float().unsqueeze(-1) * (0.5 + 2.0 ** -6) + (x.float().abs().view(xg.shape) + 1) * 2e-3
     assert bool((err <= bound).all())
     # slab vs oracle
     sl = to_np(x[1, 2]) if shape[2] > 1 else to_np(x[1, :4, 0])
