@@ -127,25 +127,27 @@ int kivi_unpack_dequant_lastdim_f16(const void* code, const void* scale, const v
  * the fp16 V window (ring buffer starting at vhead).  All sequences of the batch have the same
  * length, as in the reference (one kv_seq_len per cache, :309, :455).
  * head_dim is 128 (every model the reference ships); group_size in {32,64,128};
- * residual_length % group_size == 0 (:344) and <= 256.
+ * residual_length % group_size == 0 (:344), residual_length in {32, 64, 128, 256}.
  * ========================================================================================== */
 typedef struct kivi_cache {
     int32_t batch, num_heads, num_kv_heads, head_dim;
     int32_t k_bits, v_bits, group_size, residual_length;
     int32_t k_cap_blocks;   /* capacity of the K store in 128-token blocks   (kivi_cache_sizes out[0]) */
-    int32_t v_cap;          /* capacity of the V store in tokens             (out[1]) */
+    int32_t v_cap_blocks;   /* capacity of the V store in 128-token blocks   (out[1]) */
     int32_t v_res_cap;      /* slots of the fp16 V ring buffer               (out[2]) */
     int32_t reserved;
     void* k_store;          /* out[3] bytes */
-    void* v_codes;          /* out[4] bytes */
-    void* v_meta;           /* out[5] bytes */
-    void* k_res;            /* out[6] bytes */
-    void* v_res;            /* out[7] bytes */
+    void* v_store;          /* out[4] bytes */
+    void* k_res;            /* out[5] bytes */
+    void* v_res;            /* out[6] bytes */
     void* state;            /* device int32[8], shared by the layers of one model */
 } kivi_cache_t;
 
 /* Buffer sizes for a cache that can hold max_tokens tokens per sequence: out[0..2] = capacities
- * (k_cap_blocks, v_cap, v_res_cap), out[3..7] = bytes of k_store, v_codes, v_meta, k_res, v_res. */
+ * (k_cap_blocks, v_cap_blocks, v_res_cap), out[3..6] = bytes of k_store, v_store, k_res, v_res.
+ * Both stores are sequences of 128 x 128 "inner x outer" blocks (K: channel x token, V: token x channel;
+ * quantisation groups along the outer dim) whose codes are laid out as mma.sync A-operand fragments and
+ * whose scales / zeros are laid out as the B-fragment builders read them: kivi_b200/csrc/kivi_decode.cuh. */
 int kivi_cache_sizes(int batch, int num_kv_heads, int k_bits, int v_bits, int group_size,
                      int residual_length, int max_tokens, int64_t* out);
 
@@ -166,21 +168,18 @@ int kivi_cache_prefill_f16(const kivi_cache_t* cache, const void* k, const void*
  * `state` is READ ONLY here; call kivi_cache_advance once per step after the last layer.
  *   q [B, H, 128], k_new / v_new [B, Hkv, 128], out [B, H, 128]  fp16 contiguous
  *   mask: NULL or additive fp16 [B, kv_len + 1] (broadcast over heads, :364-372)
+ *   workspace: NULL, or fp16 [B*H, ld] (16-B aligned, ld % 8 == 0, ld >= kv_len + 1 + 8) that holds the
+ *   logits rows when they do not fit in shared memory next to the streaming stages (long contexts; with
+ *   workspace == NULL such a call returns KIVI_ERR_CAPACITY)
  *   dbg_logits / dbg_probs: NULL or fp16 [B, H, dbg_stride] receiving s and p (tests)
- *   max_kv_len: upper bound of kv_len + 1 used to size shared memory (<= what the device allows,
- *   else KIVI_ERR_CAPACITY).  Persistent grid: one CTA per SM looping over (b, kv-head) units;
- *   packed tiles stream HBM -> shared memory through cp.async.bulk (TMA) into an mbarrier ring.  */
+ *   max_kv_len: upper bound of kv_len + 1 used to size shared memory.
+ * One launch: persistent grid (2 CTAs per SM) looping over (b, kv-head, chunk of <= 4 query heads) units;
+ * every warp streams 128-token packed blocks HBM -> shared memory through cp.async.bulk (TMA) into
+ * private mbarrier stages; the contraction of a packed block runs on mma.sync (exact fp16 codes x exact
+ * hi/lo split of x*scale, fp32 accumulate), the query heads of a KV head share the MMAs (GQA). */
 int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const void* k_new, const void* v_new,
-                              const void* mask, void* out, void* dbg_logits, void* dbg_probs,
-                              int64_t dbg_stride, int max_kv_len, void* stream);
-
-/* The same decode attention as kivi_decode_attention_f16, as three barrier-free launches (q.K^T into a
- * global fp16 workspace, row softmax, p.V + cache update).  No shared-memory bound on the context
- * length; the intermediate logits / probabilities make one round trip through L2/HBM.
- *   workspace: fp16 [B*H, ld], ld % 8 == 0, ld >= kv_len + 1 + 8; on return it holds the probabilities. */
-int kivi_decode_attention_split_f16(const kivi_cache_t* cache, const void* q, const void* k_new, const void* v_new,
-                                    const void* mask, void* out, void* workspace, int64_t ld,
-                                    void* dbg_logits, void* dbg_probs, int64_t dbg_stride, void* stream);
+                              const void* mask, void* out, void* workspace, int64_t ld,
+                              void* dbg_logits, void* dbg_probs, int64_t dbg_stride, int max_kv_len, void* stream);
 
 /* Advance `state` by one token (the bookkeeping of :343-356, :386-399); once per step, all layers. */
 int kivi_cache_advance(const kivi_cache_t* cache, void* stream);

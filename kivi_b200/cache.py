@@ -18,8 +18,8 @@ class _CacheStruct(ctypes.Structure):
     """kivi_cache_t of include/kivi_b200.h"""
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("batch", "num_heads", "num_kv_heads", "head_dim", "k_bits", "v_bits", "group_size",
-                 "residual_length", "k_cap_blocks", "v_cap", "v_res_cap", "reserved")] + \
-               [(n, ctypes.c_void_p) for n in ("k_store", "v_codes", "v_meta", "k_res", "v_res", "state")]
+                 "residual_length", "k_cap_blocks", "v_cap_blocks", "v_res_cap", "reserved")] + \
+               [(n, ctypes.c_void_p) for n in ("k_store", "v_store", "k_res", "v_res", "state")]
 
 
 _BOUND = False
@@ -33,8 +33,7 @@ def _bind():
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
     _lib.bind("kivi_cache_sizes", i32, [i32] * 7 + [ctypes.POINTER(i64)])
     _lib.bind("kivi_cache_prefill_f16", i32, [P, vp, vp, i32, vp])
-    _lib.bind("kivi_decode_attention_f16", i32, [P, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp])
-    _lib.bind("kivi_decode_attention_split_f16", i32, [P, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp])
+    _lib.bind("kivi_decode_attention_f16", i32, [P, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i32, vp])
     _lib.bind("kivi_cache_advance", i32, [P, vp])
     _lib.bind("kivi_cache_export_f16", i32, [P, i32, i32, i32, i32, i32] + [vp] * 9)
     _BOUND = True
@@ -58,21 +57,23 @@ class KiviCache:
         sizes = (ctypes.c_int64 * 8)()
         _lib.check(_lib.lib().kivi_cache_sizes(batch, num_kv_heads, k_bits, v_bits, group_size, residual_length,
                                                max_tokens, sizes), "kivi_cache_sizes")
-        self.k_cap_blocks, self.v_cap, self.v_res_cap = int(sizes[0]), int(sizes[1]), int(sizes[2])
-        self._bytes = [int(s) for s in sizes[3:8]]
+        self.k_cap_blocks, self.v_cap_blocks, self.v_res_cap = int(sizes[0]), int(sizes[1]), int(sizes[2])
+        self._bytes = [int(s) for s in sizes[3:7]]                    # k_store, v_store, k_res, v_res
         self.state = torch.zeros(8, dtype=torch.int32, device=self.device)
         self._bufs, self._structs = [], []
         for _ in range(n_layers):
             bufs = [torch.zeros(nb, dtype=torch.uint8, device=self.device) for nb in self._bytes]
             st = _CacheStruct(batch, num_heads, num_kv_heads, head_dim, k_bits, v_bits, group_size, residual_length,
-                              self.k_cap_blocks, self.v_cap, self.v_res_cap, 0,
+                              self.k_cap_blocks, self.v_cap_blocks, self.v_res_cap, 0,
                               *[b.data_ptr() for b in bufs], self.state.data_ptr())
             self._bufs.append(bufs)
             self._structs.append(st)
-        # "fused": one launch per layer; "split": q.K^T / softmax / p.V launches (any context length)
+        # logits rows live in shared memory; a global fp16 workspace is allocated the first time the kernel
+        # reports that they do not fit (long contexts)
         import os
-        self.mode = os.environ.get("KIVI_ATTN_MODE", "auto")   # auto: fused while its [G][T] fp16 row fits in shared memory
         self._ws = None
+        if os.environ.get("KIVI_FORCE_WORKSPACE"):
+            self._alloc_ws()
         # host mirror of `state` (its evolution is deterministic)
         self.tk = self.r = self.tv = self.L = self.vhead = self.kv_len = 0
 
@@ -117,7 +118,7 @@ class KiviCache:
     def decode_attention(self, layer: int, q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor,
                          mask: torch.Tensor | None = None, out: torch.Tensor | None = None,
                          dbg_logits: torch.Tensor | None = None, dbg_probs: torch.Tensor | None = None,
-                         mode: str | None = None):
+                         ):
         """One fused launch: attention of q [B,H,128] over the cache + k_new/v_new [B,Hkv,128], then the
         cache update for this layer.  Call advance() once after the last layer of the step."""
         _lib.require_cuda(q, k_new, v_new)
@@ -136,35 +137,26 @@ class KiviCache:
             if d is not None:
                 assert d.dtype == torch.float16 and d.is_contiguous() and d.shape[:2] == (self.batch, self.num_heads)
                 stride = d.shape[-1]
-        mode = mode or self.mode
-        if mode == "auto":
-            try:
-                return self.decode_attention(layer, q, k_new, v_new, mask=mask, out=out, dbg_logits=dbg_logits,
-                                             dbg_probs=dbg_probs, mode="fused")
-            except _lib.KiviError as e:
-                if e.code != -8:                                   # KIVI_ERR_CAPACITY: context too long for the fused kernel
-                    raise
-                self.mode = mode = "split"
-        if mode == "split":
-            if self._ws is None:
-                ld = (self.max_tokens + 16 + 7) // 8 * 8
-                self._ws = torch.zeros((self.batch * self.num_heads, ld), dtype=torch.float16, device=self.device)
+        for attempt in (0, 1):
             with torch.cuda.device(self.device):
-                _lib.check(_lib.lib().kivi_decode_attention_split_f16(
+                rc = _lib.lib().kivi_decode_attention_f16(
                     ctypes.byref(self._structs[layer]), q.data_ptr(), k_new.data_ptr(), v_new.data_ptr(),
-                    mask.data_ptr() if mask is not None else None, out.data_ptr(), self._ws.data_ptr(), self._ws.shape[1],
+                    mask.data_ptr() if mask is not None else None, out.data_ptr(),
+                    self._ws.data_ptr() if self._ws is not None else None,
+                    self._ws.shape[1] if self._ws is not None else 0,
                     dbg_logits.data_ptr() if dbg_logits is not None else None,
-                    dbg_probs.data_ptr() if dbg_probs is not None else None, stride,
-                    _lib.stream_ptr(self.device)), "kivi_decode_attention_split_f16")
-            return out
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().kivi_decode_attention_f16(
-                ctypes.byref(self._structs[layer]), q.data_ptr(), k_new.data_ptr(), v_new.data_ptr(),
-                mask.data_ptr() if mask is not None else None, out.data_ptr(),
-                dbg_logits.data_ptr() if dbg_logits is not None else None,
-                dbg_probs.data_ptr() if dbg_probs is not None else None, stride, self.max_tokens,
-                _lib.stream_ptr(self.device)), "kivi_decode_attention_f16")
+                    dbg_probs.data_ptr() if dbg_probs is not None else None, stride, self.max_tokens,
+                    _lib.stream_ptr(self.device))
+            if rc == -8 and self._ws is None and attempt == 0:    # KIVI_ERR_CAPACITY: rows too long for shared memory
+                self._alloc_ws()
+                continue
+            _lib.check(rc, "kivi_decode_attention_f16")
+            break
         return out
+
+    def _alloc_ws(self):
+        ld = (self.max_tokens + 16 + 7) // 8 * 8
+        self._ws = torch.zeros((self.batch * self.num_heads, ld), dtype=torch.float16, device=self.device)
 
     def advance(self):
         with torch.cuda.device(self.device):

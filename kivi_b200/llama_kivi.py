@@ -423,7 +423,7 @@ class LlamaForCausalLM_KIVI(nn.Module):
                 # warm-up on a side stream (cuBLAS workspaces, lazy module loading), then capture
                 state = self.cache.state.clone()
                 pos = self._pos.clone()
-                snap = [[b.clone() for b in (bufs[3], bufs[4])] for bufs in self.cache._bufs]  # fp16 windows
+                snap = [[b.clone() for b in (bufs[2], bufs[3])] for bufs in self.cache._bufs]  # fp16 windows
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
@@ -434,8 +434,8 @@ class LlamaForCausalLM_KIVI(nn.Module):
                 self.cache.state.copy_(state)
                 self._pos.copy_(pos)
                 for bufs, (kr, vr) in zip(self.cache._bufs, snap):
-                    bufs[3].copy_(kr)
-                    bufs[4].copy_(vr)
+                    bufs[2].copy_(kr)
+                    bufs[3].copy_(vr)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._step_body()

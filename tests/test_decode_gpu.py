@@ -34,11 +34,22 @@ def _tuple_equal(got, exp):
             np.testing.assert_array_equal(a, b, err_msg=f"tuple[{i}]")
 
 
-def _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=1024, n_layers=1, mode="fused"):
+def _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=1024, n_layers=1, mode="smem"):
+    """mode "smem": logits rows in shared memory; "workspace": forced into the global workspace (the long-context path)."""
     from kivi_b200.cache import KiviCache
     c = KiviCache(n_layers, B, H, Hkv, 128, kb, vb, g, R, max_tokens)
-    c.mode = mode
+    if mode == "workspace":
+        c._alloc_ws()
     return c
+
+
+@pytest.fixture(params=["smem", "workspace"])
+def mode(request, monkeypatch):
+    if request.param == "workspace":
+        monkeypatch.setenv("KIVI_FORCE_WORKSPACE", "1")
+    else:
+        monkeypatch.delenv("KIVI_FORCE_WORKSPACE", raising=False)
+    return request.param
 
 
 @pytest.mark.parametrize("n", [1, 5, 128, 200, 333, 640])
@@ -131,7 +142,6 @@ DECODE_CASES = [  # B, H, Hkv, kb, vb, g, R, n_prefill, steps
 ]
 
 
-@pytest.mark.parametrize("mode", ["fused", "split"])
 @pytest.mark.parametrize("B,H,Hkv,kb,vb,g,R,n0,steps", DECODE_CASES)
 def test_decode_steps_match_oracle(B, H, Hkv, kb, vb, g, R, n0, steps, mode):
     rng = np.random.default_rng(n0 * 13 + H + R)
@@ -181,7 +191,6 @@ def _oracle_step(st, q, k_new, v_new, g, kb, vb, R, mask=None):
     return ref.decode_step(st, q, k_new, v_new, g, kb, vb, R, mask)
 
 
-@pytest.mark.parametrize("mode", ["fused", "split"])
 def test_decode_with_mask(mode):
     """Additive mask + max with finfo.min (models/llama_kivi.py:364-372), e.g. left padding."""
     rng = np.random.default_rng(4)
@@ -234,7 +243,6 @@ def test_multi_layer_shared_state():
         _tuple_equal(cache.export(l), sts[l])
 
 
-@pytest.mark.parametrize("mode", ["fused", "split"])
 def test_full_size_consistency(mode):
     """BASELINE cfg 2 layer shape (B32, H32, T = 4096, K2V2 g32 R128): too big for the CPU oracle end to
     end, so (1) a slab of units is checked stage-by-stage against the oracle, (2) the fused kernel must

@@ -114,12 +114,6 @@ def main():
     res["fused_bytes"] = bytes_fused
     ms2, _ = timeit(lambda: cache.decode_attention(0, qd, kn, vn, out=outd), iters=30)   # no L2 flush (cache >> L2 anyway)
     res["fused_decode_noflush_ms"] = ms2
-    bytes_split = bytes_fused + 4 * B * H * (cache.kv_len + 1) * 2                          # + logits/probs round trip
-    ms3, best3 = timeit(lambda: cache.decode_attention(0, qd, kn, vn, out=outd, mode="split"), flush=flush, iters=30)
-    res["split_decode_ms"] = ms3
-    res["split_decode_best_ms"] = best3
-    res["split_decode_GBps_algorithmic"] = bytes_fused / ms3 / 1e6
-
     if a.ref:
         kT = torch.randn((B, Hkv, D, Tk), generator=gen, device=dev, dtype=torch.float16)
         kc, ks, kz = new_pack.triton_quantize_and_pack_along_last_dim(kT, g, bits)

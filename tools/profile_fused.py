@@ -30,6 +30,6 @@ kn = torch.randn((a.B, a.Hkv, 128), generator=gen, device="cuda", dtype=torch.fl
 vn = torch.randn((a.B, a.Hkv, 128), generator=gen, device="cuda", dtype=torch.float16)
 out = torch.empty_like(q)
 for _ in range(a.iters):
-    cache.decode_attention(0, q, kn, vn, out=out, mode=a.mode)
+    cache.decode_attention(0, q, kn, vn, out=out)
 torch.cuda.synchronize()
 print("state", cache.tk, cache.r, cache.tv, cache.L)
