@@ -157,7 +157,13 @@ int kivi_cache_sizes(int batch, int num_kv_heads, int k_bits, int v_bits, int gr
  *   store (fused transpose + quantise); V: the first n - R tokens per token in groups of g channels. */
 int kivi_cache_prefill_f16(const kivi_cache_t* cache, const void* k, const void* v, int n, void* stream);
 
-/* One decode step of attention for one layer, fused (models/llama_kivi.py:314-399):
+/* Bytes of the scratch workspace kivi_decode_attention_f16 needs for this cache geometry and contexts of up to
+ * max_kv_len tokens (negative: KIVI_ERR_*).  The caller allocates it once, ZERO-INITIALISED (it holds arrival
+ * counters that every call leaves at zero), 256-B aligned; one workspace can serve all layers of a model when
+ * the layers run on one stream. */
+int64_t kivi_decode_workspace_bytes(const kivi_cache_t* cache, int max_kv_len);
+
+/* One decode step of attention for one layer (models/llama_kivi.py:314-399):
  *   logits = [ q.Kq^T (dequantise in register) | q.K_full^T | q.k_new ]   each rounded to fp16 (:324-337)
  *   s      = fp16(logits * (1/sqrt(128))) (+ mask, max with finfo.min)     (:339, :369-372)
  *   p      = fp16(softmax_fp32(s))                                          (:375)
@@ -168,17 +174,20 @@ int kivi_cache_prefill_f16(const kivi_cache_t* cache, const void* k, const void*
  * `state` is READ ONLY here; call kivi_cache_advance once per step after the last layer.
  *   q [B, H, 128], k_new / v_new [B, Hkv, 128], out [B, H, 128]  fp16 contiguous
  *   mask: NULL or additive fp16 [B, kv_len + 1] (broadcast over heads, :364-372)
- *   workspace: NULL, or fp16 [B*H, ld] (16-B aligned, ld % 8 == 0, ld >= kv_len + 1 + 8) that holds the
- *   logits rows when they do not fit in shared memory next to the streaming stages (long contexts; with
- *   workspace == NULL such a call returns KIVI_ERR_CAPACITY)
+ *   workspace / workspace_bytes: see kivi_decode_workspace_bytes (scaled logits rows, per-block softmax
+ *   statistics, partial output records, arrival counters); no bound on the context length
  *   dbg_logits / dbg_probs: NULL or fp16 [B, H, dbg_stride] receiving s and p (tests)
- *   max_kv_len: upper bound of kv_len + 1 used to size shared memory.
- * One launch: persistent grid (2 CTAs per SM) looping over (b, kv-head, chunk of <= 4 query heads) units;
- * every warp streams 128-token packed blocks HBM -> shared memory through cp.async.bulk (TMA) into
- * private mbarrier stages; the contraction of a packed block runs on mma.sync (exact fp16 codes x exact
- * hi/lo split of x*scale, fp32 accumulate), the query heads of a KV head share the MMAs (GQA). */
+ *   max_kv_len: the value the workspace was sized with (>= kv_len + 1).
+ * Two launches on `stream`, no CTA barrier in either: every warp of a persistent grid is an autonomous worker
+ * that streams 128-token packed blocks HBM -> shared memory with cp.async.bulk (TMA) into private mbarrier
+ * stages.  (1) q.K^T: items dealt round-robin; each writes its fp16 logits and (max, sum exp) statistics.
+ * (2) p.V: the (unit, block) sequence is cut into one contiguous range per warp; a warp normalises its logits
+ * slices with the row's combined statistics, accumulates, and writes one partial record per unit; the last
+ * arriver of a unit adds the records in fixed order, rounds, writes `out` and updates the cache.  The
+ * contraction of a packed block runs on mma.sync (codes as exact fp16 denormals x exact hi/lo split of
+ * x*scale, fp32 accumulate); the query heads of a KV head share the MMAs (GQA). */
 int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const void* k_new, const void* v_new,
-                              const void* mask, void* out, void* workspace, int64_t ld,
+                              const void* mask, void* out, void* workspace, int64_t workspace_bytes,
                               void* dbg_logits, void* dbg_probs, int64_t dbg_stride, int max_kv_len, void* stream);
 
 /* Advance `state` by one token (the bookkeeping of :343-356, :386-399); once per step, all layers. */

@@ -33,6 +33,7 @@ def _bind():
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
     _lib.bind("kivi_cache_sizes", i32, [i32] * 7 + [ctypes.POINTER(i64)])
     _lib.bind("kivi_cache_prefill_f16", i32, [P, vp, vp, i32, vp])
+    _lib.bind("kivi_decode_workspace_bytes", i64, [P, i32])
     _lib.bind("kivi_decode_attention_f16", i32, [P, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i32, vp])
     _lib.bind("kivi_cache_advance", i32, [P, vp])
     _lib.bind("kivi_cache_export_f16", i32, [P, i32, i32, i32, i32, i32] + [vp] * 9)
@@ -68,12 +69,12 @@ class KiviCache:
                               *[b.data_ptr() for b in bufs], self.state.data_ptr())
             self._bufs.append(bufs)
             self._structs.append(st)
-        # logits rows live in shared memory; a global fp16 workspace is allocated the first time the kernel
-        # reports that they do not fit (long contexts)
-        import os
-        self._ws = None
-        if os.environ.get("KIVI_FORCE_WORKSPACE"):
-            self._alloc_ws()
+        # scratch of the decode attention (logits rows, softmax statistics, partial records, arrival counters):
+        # one zero-initialised buffer shared by all layers (they run one after the other on the stream)
+        nws = int(_lib.lib().kivi_decode_workspace_bytes(ctypes.byref(self._structs[0]), max_tokens))
+        if nws < 0:
+            _lib.check(nws, "kivi_decode_workspace_bytes")
+        self._ws = torch.zeros(nws, dtype=torch.uint8, device=self.device)
         # host mirror of `state` (its evolution is deterministic)
         self.tk = self.r = self.tv = self.L = self.vhead = self.kv_len = 0
 
@@ -119,8 +120,9 @@ class KiviCache:
                          mask: torch.Tensor | None = None, out: torch.Tensor | None = None,
                          dbg_logits: torch.Tensor | None = None, dbg_probs: torch.Tensor | None = None,
                          ):
-        """One fused launch: attention of q [B,H,128] over the cache + k_new/v_new [B,Hkv,128], then the
-        cache update for this layer.  Call advance() once after the last layer of the step."""
+        """Attention of q [B,H,128] over the cache + k_new/v_new [B,Hkv,128], then the cache update for this
+        layer (two launches: q.K^T + statistics, then p.V + output + update).  Call advance() once after the last
+        layer of the step."""
         _lib.require_cuda(q, k_new, v_new)
         assert q.shape == (self.batch, self.num_heads, self.head_dim) and q.dtype == torch.float16
         assert k_new.shape == (self.batch, self.num_kv_heads, self.head_dim) and v_new.shape == k_new.shape
@@ -137,26 +139,15 @@ class KiviCache:
             if d is not None:
                 assert d.dtype == torch.float16 and d.is_contiguous() and d.shape[:2] == (self.batch, self.num_heads)
                 stride = d.shape[-1]
-        for attempt in (0, 1):
-            with torch.cuda.device(self.device):
-                rc = _lib.lib().kivi_decode_attention_f16(
-                    ctypes.byref(self._structs[layer]), q.data_ptr(), k_new.data_ptr(), v_new.data_ptr(),
-                    mask.data_ptr() if mask is not None else None, out.data_ptr(),
-                    self._ws.data_ptr() if self._ws is not None else None,
-                    self._ws.shape[1] if self._ws is not None else 0,
-                    dbg_logits.data_ptr() if dbg_logits is not None else None,
-                    dbg_probs.data_ptr() if dbg_probs is not None else None, stride, self.max_tokens,
-                    _lib.stream_ptr(self.device))
-            if rc == -8 and self._ws is None and attempt == 0:    # KIVI_ERR_CAPACITY: rows too long for shared memory
-                self._alloc_ws()
-                continue
-            _lib.check(rc, "kivi_decode_attention_f16")
-            break
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().kivi_decode_attention_f16(
+                ctypes.byref(self._structs[layer]), q.data_ptr(), k_new.data_ptr(), v_new.data_ptr(),
+                mask.data_ptr() if mask is not None else None, out.data_ptr(),
+                self._ws.data_ptr(), self._ws.numel(),
+                dbg_logits.data_ptr() if dbg_logits is not None else None,
+                dbg_probs.data_ptr() if dbg_probs is not None else None, stride, self.max_tokens,
+                _lib.stream_ptr(self.device)), "kivi_decode_attention_f16")
         return out
-
-    def _alloc_ws(self):
-        ld = (self.max_tokens + 16 + 7) // 8 * 8
-        self._ws = torch.zeros((self.batch * self.num_heads, ld), dtype=torch.float16, device=self.device)
 
     def advance(self):
         with torch.cuda.device(self.device):

@@ -1,4 +1,4 @@
-// kivi_attn.cuh -- fused KIVI decode attention over the blocked cache (sm_100a), one launch per layer.
+// kivi_attn.cuh -- KIVI decode attention over the blocked cache (sm_100a): two barrier-free launches.
 //
 // Replaces the ~30 launches of the reference's decode branch (models/llama_kivi.py:314-399): q.Kq^T with
 // in-register dequantisation, the fp16 K window, scale, mask, fp32 softmax, p.Vq, the fp16 V window, the
@@ -6,16 +6,21 @@
 // of the reference are reproduced (fp16 logits -> fp16 scale -> fp32 softmax -> fp16 probs -> fp16 partial
 // outputs -> fp16 add).
 //
-// Execution model
-//   * persistent grid, CTA c handles units c, c+grid, ...; unit = (b, kv-head, chunk of G query heads):
-//     packed bytes are read once per KV head for all G heads (GQA);
-//   * 8 warps per CTA, each with S PRIVATE shared-memory stages.  A warp streams its own work items
-//     HBM -> shared memory with 1-D bulk copies (cp.async.bulk = the TMA engine, SASS UBLKCP, L2
-//     evict-first) completing on the stage's mbarrier; right after consuming a stage its elected lane issues
-//     the copy of the item S positions ahead (fence.proxy.async orders its reads before the async write).
-//     The issue cursor runs ahead across the K -> softmax -> V phases and across units, so HBM never idles
-//     behind a barrier.  Items (dealt round-robin to the warps): one 128-token packed K block, <= 24 tokens of
-//     the fp16 K window, one 128-token packed V block, <= 24 tokens of the fp16 V ring.
+// Execution model: EVERY WARP IS AN AUTONOMOUS WORKER -- no CTA barrier anywhere, no per-unit tail.
+//   qk_kernel   items (dealt round-robin over all warps of the persistent grid): one 128-token packed K block,
+//               <= 24 tokens of the fp16 K window, or the new token.  An item writes its scaled fp16 logits to the
+//               workspace row and its softmax statistics (max, sum exp) to the row's statistics slots.
+//   sv_kernel   the (unit, pseudo-block) sequence [V blocks | fp16 V window items | new token] of all units is cut
+//               into one contiguous range per warp.  A warp combines the row's statistics into (M, S) -- the same
+//               instructions on the same data in every warp, hence bit-identical -- turns the logits slice of its
+//               block into fp16 probabilities in place in shared memory (they arrive with the block through the
+//               same bulk-copy group), accumulates across the blocks of a unit, and writes one partial record per
+//               unit.  The LAST warp to arrive for a unit (atomic counter) adds the records in a fixed order,
+//               rounds, writes the output and performs the unit's cache update.
+//   Data movement: each warp owns S private shared-memory stages and streams its own items HBM -> smem with
+//   1-D bulk copies (cp.async.bulk = the TMA engine, SASS UBLKCP, L2 evict-first) completing on the stage's
+//   mbarrier; right after consuming a stage its elected lane issues the copy of the item S positions ahead
+//   (fence.proxy.async orders its reads before the async write).
 //
 // Arithmetic of a packed block (128 inner x 128 outer, kivi_decode.cuh):
 //     sum_i x_i * (s_i,G * c_i,o + z_i,G) = sum_i (x_i * s_i,G) * c_i,o  +  sum_i x_i * z_i,G
@@ -37,28 +42,36 @@ namespace kivi {
 
 int make_desc(const kivi_cache_t* k, CacheDesc* d);
 
-constexpr int kCW = 8;                 // warps per CTA
+constexpr int kCW = 8;                 // warps per CTA (they never synchronise with each other)
 constexpr int kThreads = kCW * 32;
 constexpr int kResTile = 24;           // tokens per fp16-window item (24 * 256 B = 6 KB)
 constexpr int kResBytes = kResTile * kD * 2;
 constexpr float kRcpSqrtD = 1.0f / 11.313708f;   // ATen: x * (1.0f / float(math.sqrt(128)))  (llama_kivi.py:339)
-// probabilities are kept x 2^6 in the logits row during the V phase: exact, and it keeps the fp16 residual
-// fma(p, s, -hi) of small probabilities out of the denormal range
+// probabilities are kept x 2^6 while they feed the MMAs: exact, and it keeps the fp16 residual fma(p, s, -hi) of
+// small probabilities out of the denormal range
 constexpr float kProbScale = 64.f, kProbScaleInv = 1.f / 64.f;
-constexpr int kScratchBytes = 256;     // per-CTA scratch of commit_unit (V token codes)
+
+struct Workspace {                     // carved from the caller's buffer (kivi_decode_workspace_bytes)
+    __half* lg; long long ld;          // [B*H][ld] scaled logits (fp16), ld % 128 == 0
+    float2* stats; int stat_cap;       // [B*H][stat_cap] (max, sum exp(x - max)) per qk item
+    float* part; int part_cap;         // [n_units][part_cap][G][2][128] partial outputs (packed | window)
+    int* count;                        // [n_units] arrivals of sv ranges; the last arriver resets it to 0
+};
 
 struct AttnParams {
     CacheDesc c;
     const __half* q; const __half* k_new; const __half* v_new; const __half* mask;
     __half* out; __half* dbg_logits; __half* dbg_probs;
     long long dbg_stride;
-    __half* ws; long long ld;          // optional global fp16 workspace [B*H][ld] for the logits rows (long contexts)
-    int t_cap, stage_bytes, spw /*stages per warp*/, hchunks, n_units, use_ws;
+    Workspace w;
+    int stage_bytes, spw /*stages per warp*/, hchunks, n_units, nw_eff /*warps that own an sv range*/;
 };
 
 struct Sched {                          // per-step constants, identical for every unit
     int tk, r, tv, L, vhead, T, seg1;
     int n_kb, n_kr, n_vb, vr1, n_vr;
+    int ipu;                            // qk items per unit: K blocks, K window items, the new token
+    int bpu;                            // sv pseudo-blocks per unit: V blocks, V window items, the new token
 };
 
 __device__ __forceinline__ Sched make_sched(const CacheDesc& c) {
@@ -71,74 +84,25 @@ __device__ __forceinline__ Sched make_sched(const CacheDesc& c) {
     s.seg1 = min(s.L, c.v_res_cap - s.vhead);
     s.vr1 = cdiv(s.seg1, kResTile);
     s.n_vr = s.vr1 + cdiv(s.L - s.seg1, kResTile);
+    s.ipu = s.n_kb + s.n_kr + 1;
+    s.bpu = s.n_vb + s.n_vr + 1;
     return s;
 }
 
-// items are dealt round-robin: index i of a list that starts at round-robin position `base` goes to
-// warp (base + i) % kCW
-__device__ __forceinline__ int rr_first(int base, int w) { return (w - base % kCW + kCW) % kCW; }
-__device__ __forceinline__ int rr_count(int n, int first) { return n > first ? (n - first - 1) / kCW + 1 : 0; }
-
-// The item stream of one warp.  Per unit, in order:
-//   K phase:  KB(block = w + 8a) a < nkb;   KR(i = kr0 + 8b) b < nkr
-//   V phase:  VB(block = w + 8a) a < nvb;   VR(i = vr0 + 8b) b < nvr
-struct WarpPlan {
-    int nkb, nkr, kr0, nvb, nvr, vr0, per_unit;
-    __device__ __forceinline__ WarpPlan(const Sched& s, int w) {
-        nkb = rr_count(s.n_kb, w);
-        kr0 = rr_first(s.n_kb, w); nkr = rr_count(s.n_kr, kr0);
-        nvb = rr_count(s.n_vb, w);
-        vr0 = rr_first(s.n_vb, w); nvr = rr_count(s.n_vr, vr0);
-        per_unit = nkb + nkr + nvb + nvr;
-    }
-};
-
-struct Pipe {                           // a warp's private stages + its issue cursor
+struct Pipe {                           // a warp's private stages
     uint8_t* base; uint64_t* full; int spw, stage_bytes;
-    int iss_unit, iss_j, iss_n;         // next item to issue: (unit, index within the unit's list), count issued
-    __device__ __forceinline__ uint8_t* stage(int m) const { return base + (size_t)(m % spw) * stage_bytes; }
-    __device__ __forceinline__ void wait_full(int m) const { mbar_wait(&full[m % spw], (uint32_t)((m / spw) & 1)); }
-};
-
-// Issue the warp's next item (executed by the whole warp, copies issued by lane 0).
-template <int KB, int VB>
-__device__ __forceinline__ void issue_next(Pipe& pp, const AttnParams& p, const Sched& s, const WarpPlan& wp,
-                                           int warp, int lane, uint64_t pol)
-{
-    if (pp.iss_unit >= p.n_units || wp.per_unit == 0) return;
-    const CacheDesc& c = p.c;
-    const int u = pp.iss_unit / p.hchunks;
-    uint8_t* dst = pp.stage(pp.iss_n);
-    uint64_t* bar = &pp.full[pp.iss_n % pp.spw];
-    int j = pp.iss_j;
-    if (lane == 0) {
-        // order this warp's earlier generic-proxy reads of the stage before the async-proxy writes
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (j < wp.nkb) {
-            const uint32_t bb = (uint32_t)lay_block_bytes(KB, c.g);
-            mbar_expect_tx(bar, bb);
-            bulk_g2s(dst, c.k_store + ((int64_t)u * c.k_cap_blocks + (warp + kCW * j)) * bb, bb, bar, pol);
-        } else if ((j -= wp.nkb) < wp.nkr) {
-            const int t0 = (wp.kr0 + kCW * j) * kResTile, nt = min(kResTile, s.r - t0);
-            mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
-            bulk_g2s(dst, c.k_res + ((int64_t)u * c.R + t0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
-        } else if ((j -= wp.nkr) < wp.nvb) {
-            const uint32_t bb = (uint32_t)lay_block_bytes(VB, c.g);
-            mbar_expect_tx(bar, bb);
-            bulk_g2s(dst, c.v_store + ((int64_t)u * c.v_cap_blocks + (warp + kCW * j)) * bb, bb, bar, pol);
-        } else {
-            j -= wp.nvb;
-            const int i = wp.vr0 + kCW * j;
-            int slot0, nt;
-            if (i < s.vr1) { const int t0 = i * kResTile; slot0 = s.vhead + t0; nt = min(kResTile, s.seg1 - t0); }
-            else { const int t0 = (i - s.vr1) * kResTile; slot0 = t0; nt = min(kResTile, s.L - s.seg1 - t0); }
-            mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
-            bulk_g2s(dst, c.v_res + ((int64_t)u * c.v_res_cap + slot0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
-        }
+    int c_stage, c_par;                 // consumer: current stage and its mbarrier parity
+    int i_stage;                        // producer: stage of the next copy
+    __device__ __forceinline__ void init(uint8_t* b, uint64_t* f, int spw_, int sb) {
+        base = b; full = f; spw = spw_; stage_bytes = sb; c_stage = 0; c_par = 0; i_stage = 0;
     }
-    ++pp.iss_n;
-    if (++pp.iss_j == wp.per_unit) { pp.iss_j = 0; pp.iss_unit += gridDim.x; }
-}
+    __device__ __forceinline__ uint8_t* cons() const { return base + (size_t)c_stage * stage_bytes; }
+    __device__ __forceinline__ void wait() const { mbar_wait(&full[c_stage], (uint32_t)c_par); }
+    __device__ __forceinline__ void pop() { if (++c_stage == spw) { c_stage = 0; c_par ^= 1; } }
+    __device__ __forceinline__ uint8_t* prod() const { return base + (size_t)i_stage * stage_bytes; }
+    __device__ __forceinline__ uint64_t* prod_bar() const { return &full[i_stage]; }
+    __device__ __forceinline__ void push() { if (++i_stage == spw) i_stage = 0; }
+};
 
 // logits (fp16 kernel output) -> fp16 scaled, the value that enters the softmax
 __device__ __forceinline__ __half scale_logit(float acc) {
@@ -242,8 +206,11 @@ __device__ __forceinline__ void gather_z(const float (&zc)[4], int lane, float (
         zsel[grp] = __shfl_sync(0xffffffffu, zc[0], 8 * grp + (lane & 3));
 }
 
-// Hand every (outer row, value) this lane owns to `emit`: value = ((hi + lo) * 2^(24-P) + Z) * post for its head
-// t % G.  Lane (g8, t) owns rows g8 / g8+8 of the MMAs whose group-in-fragment is t / G.
+// Hand every (slot, outer row, value) this lane owns to `emit`: value = ((hi + lo) * 2^(24-P) + Z) * post for its
+// head t % G; `slot` is a compile-time index (< kSlots) of the value within the lane.  Lane (g8, t) owns rows
+// g8 / g8+8 of the MMAs whose group-in-fragment is t / G.
+template <int G, int GS> struct Slots { static constexpr int k = (G == 1 && GS == 32) ? 4 : 16; };
+
 template <int BITS, int G, int GS, class EF>
 __device__ __forceinline__ void finalize(const float (&acc)[8][4], const float (&zsel)[Cols<G, GS>::NG], int lane,
                                          float post, EF&& emit)
@@ -262,10 +229,10 @@ __device__ __forceinline__ void finalize(const float (&acc)[8][4], const float (
         const float sh = (t == 0 ? inv_pos_scale<BITS>(1) : t == 1 ? inv_pos_scale<BITS>(3) : t == 2 ? inv_pos_scale<BITS>(5) : inv_pos_scale<BITS>(7)) * post;
         const float zt = (t == 0 ? zsel[0] : t == 1 ? zsel[1] : t == 2 ? zsel[2] : zsel[3]) * post;
         const int o = 32 * t + g8;
-        emit(o, fmaf(lo[0] + lo[1], sl, zt));
-        emit(o + 8, fmaf(lo[2] + lo[3], sl, zt));
-        emit(o + 16, fmaf(hi[0] + hi[1], sh, zt));
-        emit(o + 24, fmaf(hi[2] + hi[3], sh, zt));
+        emit(0, o, fmaf(lo[0] + lo[1], sl, zt));
+        emit(1, o + 8, fmaf(lo[2] + lo[3], sl, zt));
+        emit(2, o + 16, fmaf(hi[0] + hi[1], sh, zt));
+        emit(3, o + 24, fmaf(hi[2] + hi[3], sh, zt));
     } else {
         const int gi_l = t / G;
         #pragma unroll
@@ -273,36 +240,55 @@ __device__ __forceinline__ void finalize(const float (&acc)[8][4], const float (
             const int grp = (16 * mm) / GS;
             if (grp % GPF == gi_l) {
                 const float sc = inv_pos_scale<BITS>(mm) * post, zt = zsel[grp] * post;
-                emit(16 * mm + g8, fmaf(acc[mm][0] + acc[mm][1], sc, zt));
-                emit(16 * mm + g8 + 8, fmaf(acc[mm][2] + acc[mm][3], sc, zt));
+                emit(2 * mm, 16 * mm + g8, fmaf(acc[mm][0] + acc[mm][1], sc, zt));
+                emit(2 * mm + 1, 16 * mm + g8 + 8, fmaf(acc[mm][2] + acc[mm][3], sc, zt));
             }
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// cache data movement of one unit (models/llama_kivi.py:343-356, :386-399); cold path, kept out of line.
-// Executed by ALL threads of the CTA (it contains CTA barriers on the K-flush path, taken uniformly).
-//   scratch: kScratchBytes private to this call; flush_scratch: >= 4 KB, free after a CTA barrier
-// ------------------------------------------------------------------------------------------------
+// the same ownership walk over per-lane slot values (the running sums of the p.V kernel)
+template <int G, int GS, class EF>
+__device__ __forceinline__ void walk_slots(const float (&run)[Slots<G, GS>::k], int lane, EF&& emit)
+{
+    constexpr int GPF = Cols<G, GS>::GPF;
+    const int g8 = lane >> 2, t = lane & 3;
+    if (G == 1 && GS == 32) {
+        #pragma unroll
+        for (int e = 0; e < 4; ++e) emit(32 * t + g8 + 8 * e, run[e]);
+    } else {
+        const int gi_l = t / G;
+        #pragma unroll
+        for (int mm = 0; mm < 8; ++mm) {
+            if (((16 * mm) / GS) % GPF == gi_l) {
+                emit(16 * mm + g8, run[2 * mm]);
+                emit(16 * mm + g8 + 8, run[2 * mm + 1]);
+            }
+        }
+    }
+}
+
+// quantise one value with its group's (min, scale): quant/new_pack.py:238-241 (rint follows)
 __device__ __forceinline__ float q_code(float x, float mnf, float scf, float maxq) {
     const __half t1 = __float2half_rn(x - mnf);
     const __half t2 = __float2half_rn(__fdiv_rn(__half2float(t1), scf));
-    return fminf(fmaxf(__half2float(t2), 0.f), maxq);       // quant/new_pack.py:238-241 (rint follows)
+    return fminf(fmaxf(__half2float(t2), 0.f), maxq);
 }
 
+// ------------------------------------------------------------------------------------------------
+// cache data movement of one unit (models/llama_kivi.py:343-356, :386-399), executed by ONE warp (the last
+// arriver of the unit); cold path, kept out of line.  scratch: 128 bytes of shared memory private to the warp.
+// ------------------------------------------------------------------------------------------------
 template <int KB, int VB>
-__device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, int u, int tid, uint8_t* scratch,
-                                         uint8_t* flush_scratch)
+__device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, int u, int lane, uint8_t* scratch)
 {
     const CacheDesc& c = p.c;
-    const int warp = tid >> 5, lane = tid & 31;
     const int g = c.g;
     // ---- V: v_new joins the ring; if the window would exceed R, its oldest token is quantised per token
-    if (tid < kD / 8)
-        reinterpret_cast<uint4*>(c.v_res + ((int64_t)u * c.v_res_cap + (s.vhead + s.L) % c.v_res_cap) * kD)[tid] =
-            __ldg(reinterpret_cast<const uint4*>(p.v_new + (int64_t)u * kD) + tid);
-    if (s.L + 1 > c.R && warp == 1) {
+    if (lane < kD / 8)
+        reinterpret_cast<uint4*>(c.v_res + ((int64_t)u * c.v_res_cap + (s.vhead + s.L) % c.v_res_cap) * kD)[lane] =
+            __ldg(reinterpret_cast<const uint4*>(p.v_new + (int64_t)u * kD) + lane);
+    if (s.L + 1 > c.R) {
         constexpr int F = 16 / VB, kSlabRows = 16 * F, kSlabs = 128 / kSlabRows;
         const float maxq = (float)((1 << VB) - 1);
         const __half* src = c.v_res + ((int64_t)u * c.v_res_cap + s.vhead) * kD;
@@ -325,6 +311,7 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
         uint32_t four = 0;
         #pragma unroll
         for (int e = 0; e < 4; ++e) four |= (uint32_t)__float2int_rn(q_code(x[e], mnf, scf, maxq)) << (8 * e);
+        __syncwarp();
         reinterpret_cast<uint32_t*>(scratch)[lane] = four;                              // codes[channel] as bytes
         if (lane % lpg == 0) {
             *reinterpret_cast<__half*>(blk + lay_scale_off(VB, g, inner, lane / lpg)) = sc;
@@ -342,158 +329,266 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
     }
     // ---- K: k_new joins the window, or completes it -> quantise the R tokens per channel
     if (s.r + 1 < c.R) {
-        if (tid >= 16 && tid < 16 + kD / 8)
-            reinterpret_cast<uint4*>(c.k_res + ((int64_t)u * c.R + s.r) * kD)[tid - 16] =
-                __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (tid - 16));
+        if (lane >= 16)
+            reinterpret_cast<uint4*>(c.k_res + ((int64_t)u * c.R + s.r) * kD)[lane - 16] =
+                __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (lane - 16));
     } else {
-        constexpr int F = 16 / KB, kSlabRows = 16 * F, kSlabs = 128 / kSlabRows;
+        // once per R steps.  A lane owns channels d = lane + 32 i; per (channel, group of g tokens): min / max, then
+        // chunks of 16 consecutive tokens = one field position j in the 16 half-words (row = token % 16) of (d, slab).
+        constexpr int F = 16 / KB, kSlabRows = 16 * F;
         const float maxq = (float)((1 << KB) - 1);
         const int bb = lay_block_bytes(KB, g);
         uint8_t* ub = c.k_store + (int64_t)u * c.k_cap_blocks * bb;
         const __half* win = c.k_res + (int64_t)u * c.R * kD;
         const __half* knew = p.k_new + (int64_t)u * kD;
-        __half2* stats = reinterpret_cast<__half2*>(flush_scratch);                     // [R/g][128] (scale, mn)
         auto tokval = [&](int t, int d) -> float {
             return __half2float(t < c.R - 1 ? win[(int64_t)t * kD + d] : knew[d]);
         };
-        __syncthreads();                                                                // flush_scratch is free now
-        for (int w = tid; w < kD * (c.R / g); w += kThreads) {
-            const int d = w % kD, grp = w / kD;
-            float mnf = tokval(grp * g, d), mxf = mnf;
-            for (int i = 1; i < g; ++i) { const float x = tokval(grp * g + i, d); mnf = fminf(mnf, x); mxf = fmaxf(mxf, x); }
-            const __half d16 = __float2half_rn(mxf - mnf);
-            const __half sc = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
-            const __half mn = __float2half_rn(mnf);
-            stats[w] = __halves2half2(sc, mn);
-            const int tok = s.tk + grp * g;
-            uint8_t* blk = ub + (int64_t)(tok / kBlockTokens) * bb;
-            *reinterpret_cast<__half*>(blk + lay_scale_off(KB, g, d, (tok % kBlockTokens) / g)) = sc;
-            *reinterpret_cast<__half*>(blk + lay_zero_off(KB, g, d, (tok % kBlockTokens) / g)) = mn;
-        }
-        __syncthreads();
-        const int nblk = max(1, c.R / kBlockTokens);                                    // R in {32, 64, 128, 256}
-        for (int bi = 0; bi < nblk; ++bi) {
-            const int tb = s.tk + bi * kBlockTokens;                                    // first flushed token of this block
-            const int o0 = tb % kBlockTokens, cnt = min(c.R, kBlockTokens);
-            uint8_t* blk = ub + (int64_t)(tb / kBlockTokens) * bb;
-            for (int id = tid; id < kD * kSlabs * 16; id += kThreads) {                 // one 16-bit half-word per item
-                const int d = id % kD, row = (id / kD) % 16, sl = id / (kD * 16);
-                uint16_t* hp = reinterpret_cast<uint16_t*>(blk + lay_word_off(KB, d, sl * kSlabRows + row) + 2 * (d & 1));
-                uint32_t hw = *hp;
+        #pragma unroll 1
+        for (int d = lane; d < kD; d += 32) {
+            #pragma unroll 1
+            for (int grp = 0; grp < c.R / g; ++grp) {
+                float mnf = tokval(grp * g, d), mxf = mnf;
+                #pragma unroll 4
+                for (int i = 1; i < g; ++i) { const float x = tokval(grp * g + i, d); mnf = fminf(mnf, x); mxf = fmaxf(mxf, x); }
+                const __half d16 = __float2half_rn(mxf - mnf);
+                const __half sc = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
+                const float scf = __half2float(sc);
+                const int tok0 = s.tk + grp * g;                                        // absolute token of the group's first element
+                uint8_t* blk = ub + (int64_t)(tok0 / kBlockTokens) * bb;
+                *reinterpret_cast<__half*>(blk + lay_scale_off(KB, g, d, (tok0 % kBlockTokens) / g)) = sc;
+                *reinterpret_cast<__half*>(blk + lay_zero_off(KB, g, d, (tok0 % kBlockTokens) / g)) = __float2half_rn(mnf);
                 #pragma unroll 1
-                for (int j = 0; j < F; ++j) {
-                    const int o = sl * kSlabRows + 16 * j + row;
-                    if (o < o0 || o >= o0 + cnt) continue;
-                    const int tl = (tb - s.tk) + (o - o0);                              // token index within the window
-                    const float2 sm = __half22float2(stats[(tl / g) * kD + d]);
-                    const uint32_t code = (uint32_t)__float2int_rn(q_code(tokval(tl, d), sm.y, sm.x, maxq));
-                    hw = (hw & ~(((1u << KB) - 1u) << (KB * j))) | (code << (KB * j));
+                for (int q16 = 0; q16 < g / 16; ++q16) {
+                    const int o0 = (tok0 % kBlockTokens) + 16 * q16;                    // outer index of row 0 of this chunk
+                    const int sl = o0 / kSlabRows, j = (o0 % kSlabRows) / 16;
+                    #pragma unroll 4
+                    for (int row = 0; row < 16; ++row) {
+                        const uint32_t code = (uint32_t)__float2int_rn(q_code(tokval(grp * g + 16 * q16 + row, d), mnf, scf, maxq));
+                        uint16_t* hp = reinterpret_cast<uint16_t*>(blk + lay_word_off(KB, d, sl * kSlabRows + row) + 2 * (d & 1));
+                        *hp = (uint16_t)((*hp & ~(((1u << KB) - 1u) << (KB * j))) | (code << (KB * j)));
+                    }
                 }
-                *hp = (uint16_t)hw;
             }
         }
     }
 }
 
+// fp32 softmax statistics of up to 32 * N values held by the warp (v < -60000 marks "no value")
+__device__ __forceinline__ void warp_max_sum(float mx, float sm, float& M, float& S) {
+    // (max, sum) pairs combined over the lanes
+    #pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, mx, o), so = __shfl_xor_sync(0xffffffffu, sm, o);
+        const float mn = fmaxf(mx, mo);
+        sm = (mx == -INFINITY ? 0.f : sm * __expf(mx - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
+        mx = mn;
+    }
+    M = mx; S = sm;
+}
+
+// add the mask (models/llama_kivi.py:369-372) to a scaled fp16 logit
+__device__ __forceinline__ __half apply_mask(__half v, const __half* mask, int64_t idx) {
+    v = __hadd_rn(v, mask[idx]);
+    if (__half2float(v) < -65504.f) v = __float2half_rn(-65504.f);
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// work split: the (unit, pseudo-block) sequence of the whole job, gb = unit * per_unit + j, is cut into one
+// contiguous range per warp: warp w of the W range owners handles [lo(w), lo(w+1)), lo(w) = floor(w * N / W).
+// W <= N, so every range is non-empty and a unit of L pseudo-blocks meets at most ceil(L * W / N) + 1 ranges.
 // ------------------------------------------------------------------------------------------------
-template <int KB, int VB, int G, int GS, bool WS>
+__device__ __forceinline__ long long range_lo(long long w, long long N, long long W) { return w * N / W; }
+__device__ __forceinline__ int range_owner(long long gb, long long N, long long W) { return (int)(((gb + 1) * W - 1) / N); }
+
+// online softmax statistics: fold the values x[0..n) (any of them may be -inf = "no value") into (m, s)
+template <int N_>
+__device__ __forceinline__ void fold_stats(float& m, float& s, const float (&x)[N_]) {
+    float mn = m;
+    #pragma unroll
+    for (int e = 0; e < N_; ++e) mn = fmaxf(mn, x[e]);
+    if (mn == -INFINITY) return;
+    float acc = s * __expf(m - mn);                     // m == -inf -> s * 0
+    #pragma unroll
+    for (int e = 0; e < N_; ++e) acc += __expf(x[e] - mn);
+    m = mn; s = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// q . K^T  (+ scale, mask, per-range softmax statistics)
+// ------------------------------------------------------------------------------------------------
+template <int KB>
+__device__ __forceinline__ void qk_issue_next(Pipe& pp, long long& cur, long long hi, const AttnParams& p, const Sched& s,
+                                              int lane, uint64_t pol)
+{
+    const CacheDesc& c = p.c;
+    while (cur < hi && (int)(cur % s.ipu) == s.ipu - 1) ++cur;    // the new token needs no load
+    if (cur >= hi) return;
+    const int unit = (int)(cur / s.ipu), j = (int)(cur % s.ipu);
+    const int u = p.hchunks == 1 ? unit : unit / p.hchunks;
+    if (lane == 0) {
+        uint8_t* dst = pp.prod();
+        uint64_t* bar = pp.prod_bar();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (j < s.n_kb) {
+            const uint32_t bb = (uint32_t)lay_block_bytes(KB, c.g);
+            mbar_expect_tx(bar, bb);
+            bulk_g2s(dst, c.k_store + ((int64_t)u * c.k_cap_blocks + j) * bb, bb, bar, pol);
+        } else {
+            const int t0 = (j - s.n_kb) * kResTile, nt = min(kResTile, s.r - t0);
+            mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
+            bulk_g2s(dst, c.k_res + ((int64_t)u * c.R + t0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
+        }
+    }
+    pp.push();
+    ++cur;
+}
+
+template <int KB, int G, int GS>
 __global__ void __launch_bounds__(kThreads, 2)
-attention_kernel(const AttnParams p)
+qk_kernel(const AttnParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const CacheDesc& c = p.c;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g8 = lane >> 2, t4 = lane & 3;
+    const int t4 = lane & 3;
     const int n_stages = kCW * p.spw;
-    using CL = Cols<G, GS>;
-    constexpr int NG = CL::NG, GPF = CL::GPF;
-
-    // carve shared memory
     uint64_t* full_all = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * p.stage_bytes);
     uint8_t* ptr = smem + (((size_t)n_stages * (p.stage_bytes + 8) + 127) & ~(size_t)127);
-    uint2* q2 = reinterpret_cast<uint2*>(ptr); ptr += G * 32 * 8;    // [G][8 chunks][4 t] {q(16c+2t,+1), q(16c+2t+8,+9)} half2 pairs
-    float* qlin = reinterpret_cast<float*>(ptr); ptr += G * kD * 4;  // [G][128] q in fp32, channel order
-    float* stats = reinterpret_cast<float*>(ptr); ptr += 16 * 4;     // softmax block-reduce scratch
-    float* pnew = reinterpret_cast<float*>(ptr); ptr += 16 * 4;      // probability of the new token, per head
-    uint8_t* scratch = ptr; ptr += kScratchBytes;
-    float* red = reinterpret_cast<float*>(ptr);                      // [kCW][G][2][128] partial outputs
-    // logits row(s): [G][t_cap] scaled logits, then probabilities x 2^6 -- in shared memory (aliasing `red`, which
-    // is only written after the last read of the probabilities) or in the caller's global workspace
-    const long long lg_stride = WS ? p.ld : (long long)p.t_cap;
+    uint2* q2 = reinterpret_cast<uint2*>(ptr) + warp * (G * 32);             // per warp: [G][8 chunks][4 t] half2 pairs
+    float* qlin = reinterpret_cast<float*>(ptr + kCW * G * 32 * 8) + warp * (G * kD);   // per warp: [G][128] fp32
 
     if (tid == 0) {
         for (int i = 0; i < n_stages; ++i) mbar_init(&full_all[i], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncthreads();                                                         // the only CTA barrier: mbarrier init
 
     const Sched s = make_sched(c);
-    const WarpPlan wp(s, warp);
     const uint64_t pol = policy_evict_first();
+    const int gw = blockIdx.x * kCW + warp;
+    const long long N = (long long)p.n_units * s.ipu;                        // pseudo-blocks of the whole job
+    const long long W = min((long long)p.nw_eff, N);
+    if (gw >= W) return;
+    const long long lo = range_lo(gw, N, W), hi = range_lo(gw + 1, N, W);
     Pipe pp;
-    pp.base = smem + (size_t)warp * p.spw * p.stage_bytes;
-    pp.full = full_all + warp * p.spw;
-    pp.spw = p.spw; pp.stage_bytes = p.stage_bytes;
-    pp.iss_unit = blockIdx.x; pp.iss_j = 0; pp.iss_n = 0;
-    for (int i = 0; i < p.spw; ++i) issue_next<KB, VB>(pp, p, s, wp, warp, lane, pol);
+    pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
+    long long cur = lo;
+    for (int i = 0; i < p.spw; ++i) qk_issue_next<KB>(pp, cur, hi, p, s, lane, pol);
 
+    constexpr int NG = Cols<G, GS>::NG;
     const int ratio = c.H / c.Hkv;
-    const int h_l = t4 % G;                                         // the head this lane finalises
-    int m = 0;                                                      // items consumed so far by this warp
-    #pragma unroll 1
-    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
-        const int u = unit / p.hchunks, hc = unit % p.hchunks;
-        const int b = u / c.Hkv;
-        const int uq0 = u * ratio + hc * G;                         // first query head row of this chunk
-        __half* lg = reinterpret_cast<__half*>(red);
-        if (WS) lg = p.ws + (int64_t)uq0 * p.ld;
+    const int h_l = t4 % G;
+    const bool slow = p.mask || p.dbg_logits;                                // mask / debug copies: rare, off the fast path
 
-        // -- stage q: fp32 in channel order (window items) and the half2 pairs of the B fragments
-        for (int i = tid; i < G * kD; i += kThreads) qlin[i] = __half2float(p.q[(int64_t)uq0 * kD + i]);
-        for (int i = tid; i < G * 32; i += kThreads) {
+    long long gb = lo;
+    #pragma unroll 1
+    while (gb < hi) {
+        const int unit = (int)(gb / s.ipu);
+        const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
+        const int b = u / c.Hkv;
+        const int uq0 = u * ratio + hc * G;
+        const long long gb_end = min(hi, (long long)(unit + 1) * s.ipu);     // this warp's pseudo-blocks of this unit
+
+        // ---- this warp's copy of q: half2 pairs in B-fragment order, fp32 in channel order
+        __syncwarp();
+        for (int i = lane; i < G * 32; i += 32) {
             const int h = i >> 5, cc = (i >> 2) & 7, tt = i & 3;
             const uint32_t* qh = reinterpret_cast<const uint32_t*>(p.q + (int64_t)(uq0 + h) * kD + 16 * cc + 2 * tt);
             q2[i] = make_uint2(__ldg(qh), __ldg(qh + 4));
         }
-        __syncthreads();
-
-        // ================= K phase =================
-        #pragma unroll 1
-        for (int a = 0; a < wp.nkb; ++a) {
-            const int blk = warp + kCW * a;
-            float acc[8][4];
-            float zc[4] = {0.f, 0.f, 0.f, 0.f};
-            #pragma unroll
-            for (int mm = 0; mm < 8; ++mm)
-                #pragma unroll
-                for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
-            pp.wait_full(m);
-            mma_block<KB, G, GS>(pp.stage(m), [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
-                const uint2 v = q2[(h * 8 + cc) * 4 + t4];
-                xa = v.x; xb = v.y;
-            }, acc, zc, lane);
-            __syncwarp();
-            issue_next<KB, VB>(pp, p, s, wp, warp, lane, pol);
-            ++m;
-            float zsel[NG];
-            gather_z<G, GS>(zc, lane, zsel);
-            __half* row = lg + (int64_t)h_l * lg_stride + blk * kBlockTokens;
-            const int nvalid = s.tk - blk * kBlockTokens;             // < 128 only in the last block when R < 128
-            finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int o, float v) {
-                if (o < nvalid) row[o] = scale_logit(v);
-            });
+        #pragma unroll
+        for (int h = 0; h < G; ++h) {
+            const uint2 qv = __ldg(reinterpret_cast<const uint2*>(p.q + (int64_t)(uq0 + h) * kD) + lane);
+            const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+            const float2 a = __half22float2(qh[0]), b2 = __half22float2(qh[1]);
+            *reinterpret_cast<float4*>(qlin + h * kD + lane * 4) = make_float4(a.x, a.y, b2.x, b2.y);
         }
-        // fp16 K window
-        {
-            const int part = lane & 7, tok = lane >> 3;
-            #pragma unroll 1
-            for (int bq = 0; bq < wp.nkr; ++bq) {
-                const int i = wp.kr0 + kCW * bq;
-                const int t0 = i * kResTile, nt = min(kResTile, s.r - t0);
-                pp.wait_full(m);
-                const uint8_t* st = pp.stage(m);
+        __syncwarp();
+
+        // lane-local online softmax statistics: (m_blk, s_blk) over the packed-block logits of head h_l held by this lane,
+        // (mw[h], sw[h]) over the window / new-token logits this lane wrote for head h
+        float m_blk = -INFINITY, s_blk = 0.f;
+        float mw[G], sw[G];
+        #pragma unroll
+        for (int h = 0; h < G; ++h) { mw[h] = -INFINITY; sw[h] = 0.f; }
+
+        #pragma unroll 1
+        for (; gb < gb_end; ++gb) {
+            const int j = (int)(gb - (long long)unit * s.ipu);
+            if (j < s.n_kb) {                                                // ---- packed K block (tensor cores)
+                float acc[8][4];
+                float zc[4] = {0.f, 0.f, 0.f, 0.f};
+                #pragma unroll
+                for (int mm = 0; mm < 8; ++mm)
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
+                pp.wait();
+                mma_block<KB, G, GS>(pp.cons(), [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
+                    const uint2 v = q2[(h * 8 + cc) * 4 + t4];
+                    xa = v.x; xb = v.y;
+                }, acc, zc, lane);
+                __syncwarp();
+                pp.pop();
+                qk_issue_next<KB>(pp, cur, hi, p, s, lane, pol);
+                float zsel[NG];
+                gather_z<G, GS>(zc, lane, zsel);
+                const int64_t rowi = uq0 + h_l;
+                __half* row = p.w.lg + rowi * p.w.ld + j * kBlockTokens;
+                const int nvalid = s.tk - j * kBlockTokens;                  // < 128 only in the last block when R < 128
+                if (!slow && nvalid >= kBlockTokens) {
+                    if (G == 1 && GS == 32) {                                // exactly four logits per lane
+                        float x[4];
+                        finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int o, float v) {
+                            const __half hv = scale_logit(v);
+                            row[o] = hv;
+                            x[slot] = __half2float(hv);
+                        });
+                        fold_stats(m_blk, s_blk, x);
+                    } else {
+                        float mx = m_blk;
+                        finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
+                            const __half hv = scale_logit(v);
+                            row[o] = hv;
+                            mx = fmaxf(mx, __half2float(hv));
+                        });
+                        if (mx != -INFINITY) {
+                            float a2 = s_blk * __expf(m_blk - mx);
+                            finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
+                                a2 += __expf(__half2float(scale_logit(v)) - mx);
+                            });
+                            m_blk = mx; s_blk = a2;
+                        }
+                    }
+                } else {
+                    auto logit_of = [&](int o, float v) -> __half {          // fp16 scaled (+ mask): the softmax input
+                        __half hv = scale_logit(v);
+                        if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + j * kBlockTokens + o);
+                        return hv;
+                    };
+                    float mx = m_blk;
+                    finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
+                        if (o < nvalid) {
+                            const __half hv = logit_of(o, v);
+                            row[o] = hv;
+                            if (p.dbg_logits) p.dbg_logits[rowi * p.dbg_stride + j * kBlockTokens + o] = hv;
+                            mx = fmaxf(mx, __half2float(hv));
+                        }
+                    });
+                    if (mx != -INFINITY) {
+                        float a2 = s_blk * __expf(m_blk - mx);
+                        finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
+                            if (o < nvalid) a2 += __expf(__half2float(logit_of(o, v)) - mx);
+                        });
+                        m_blk = mx; s_blk = a2;
+                    }
+                }
+            } else if (j < s.ipu - 1) {                                      // ---- fp16 K window item
+                const int part = lane & 7, tok = lane >> 3;
+                const int t0 = (j - s.n_kb) * kResTile, nt = min(kResTile, s.r - t0);
+                pp.wait();
+                const uint8_t* st = pp.cons();
                 #pragma unroll 1
                 for (int ts = 0; ts < nt; ts += 4) {
                     const int t = ts + tok;
@@ -522,16 +617,21 @@ attention_kernel(const AttnParams p)
                         sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
                         sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 2);
                         sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 4);
-                        if (part == 0 && t < nt)
-                            lg[(int64_t)h * lg_stride + s.tk + t0 + t] = scale_logit(sum[h]);
+                        if (part == 0 && t < nt) {
+                            __half hv = scale_logit(sum[h]);
+                            const int64_t rowi = uq0 + h;
+                            if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + s.tk + t0 + t);
+                            p.w.lg[rowi * p.w.ld + s.tk + t0 + t] = hv;
+                            if (p.dbg_logits) p.dbg_logits[rowi * p.dbg_stride + s.tk + t0 + t] = hv;
+                            const float x1[1] = {__half2float(hv)};
+                            fold_stats(mw[h], sw[h], x1);
+                        }
                     }
                 }
                 __syncwarp();
-                issue_next<KB, VB>(pp, p, s, wp, warp, lane, pol);
-                ++m;
-            }
-            // the new token (k_new, not yet in the window): one warp, plain loads
-            if ((s.n_kb + s.n_kr) % kCW == warp) {
+                pp.pop();
+                qk_issue_next<KB>(pp, cur, hi, p, s, lane, pol);
+            } else {                                                         // ---- the new token
                 const uint2 kv = __ldg(reinterpret_cast<const uint2*>(p.k_new + (int64_t)u * kD) + lane);
                 const __half2* kh = reinterpret_cast<const __half2*>(&kv);
                 const float2 k01 = __half22float2(kh[0]), k23 = __half22float2(kh[1]);
@@ -541,181 +641,306 @@ attention_kernel(const AttnParams p)
                     float sum = qv.x * k01.x;
                     sum = fmaf(qv.y, k01.y, sum); sum = fmaf(qv.z, k23.x, sum); sum = fmaf(qv.w, k23.y, sum);
                     sum = warp_sum(sum);
-                    if (lane == 0) lg[(int64_t)h * lg_stride + s.T - 1] = scale_logit(sum);
-                    if (lane >= 1 && lane < 8) lg[(int64_t)h * lg_stride + s.T - 1 + lane] = __float2half_rn(-65504.f);   // pad: exp -> 0
+                    if (lane == 0) {
+                        __half hv = scale_logit(sum);
+                        const int64_t rowi = uq0 + h;
+                        if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + s.T - 1);
+                        p.w.lg[rowi * p.w.ld + s.T - 1] = hv;
+                        if (p.dbg_logits) p.dbg_logits[rowi * p.dbg_stride + s.T - 1] = hv;
+                        const float x1[1] = {__half2float(hv)};
+                        fold_stats(mw[h], sw[h], x1);
+                    }
                 }
             }
         }
-        __syncthreads();
 
-        // ================= softmax (fp32), one block-wide reduction per head =================
-        #pragma unroll 1
-        for (int h = 0; h < G; ++h) {
-            __half* row = lg + (int64_t)h * lg_stride;
-            const bool slow = p.mask || p.dbg_logits || p.dbg_probs;
-            const int nvec = (s.T + 7) >> 3;                        // the row is padded with -65504 up to 8 * nvec
-            float ml = -INFINITY, sl = 0.f;
-            if (slow) {
-                for (int t = tid; t < s.T; t += kThreads) {
-                    __half v = row[t];
-                    if (p.mask) {
-                        v = __hadd_rn(v, p.mask[(int64_t)b * s.T + t]);                   // llama_kivi.py:369
-                        if (__half2float(v) < -65504.f) v = __float2half_rn(-65504.f);    // :370-372 (max with finfo.min)
-                        row[t] = v;
-                    }
-                    if (p.dbg_logits) p.dbg_logits[(int64_t)(uq0 + h) * p.dbg_stride + t] = v;
-                    ml = fmaxf(ml, __half2float(v));
-                }
-                for (int t = tid; t < s.T; t += kThreads) sl += __expf(__half2float(row[t]) - ml);
-            } else {
-                for (int i = tid; i < nvec; i += kThreads) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(row + 8 * i);
-                    const __half2* hh = reinterpret_cast<const __half2*>(&u);
-                    #pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); ml = fmaxf(ml, fmaxf(f.x, f.y)); }
-                }
-                for (int i = tid; i < nvec; i += kThreads) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(row + 8 * i);
-                    const __half2* hh = reinterpret_cast<const __half2*>(&u);
-                    #pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); sl += __expf(f.x - ml) + __expf(f.y - ml); }
-                }
-            }
-            // (max, sum) pairs: warp, then block
-            #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const float mo = __shfl_xor_sync(0xffffffffu, ml, o), so = __shfl_xor_sync(0xffffffffu, sl, o);
-                const float mn = fmaxf(ml, mo);
-                sl = (ml == -INFINITY ? 0.f : sl * __expf(ml - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
-                ml = mn;
-            }
-            if (lane == 0) { stats[warp] = ml; stats[8 + warp] = sl; }
-            __syncthreads();
-            float M = stats[0];
-            #pragma unroll
-            for (int w = 1; w < kCW; ++w) M = fmaxf(M, stats[w]);
-            float S = 0.f;
-            #pragma unroll
-            for (int w = 0; w < kCW; ++w) S += stats[w] == -INFINITY ? 0.f : stats[8 + w] * __expf(stats[w] - M);
-            if (slow) {
-                for (int t = tid; t < s.T; t += kThreads) {
-                    const __half pr = __float2half_rn(__fdiv_rn(__expf(__half2float(row[t]) - M), S));   // :375
-                    row[t] = __float2half_rn(__half2float(pr) * kProbScale);                            // exact
-                    if (p.dbg_probs) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + t] = pr;
-                    if (t == s.T - 1) pnew[h] = __half2float(pr);
-                }
-            } else {
-                const float rS = __frcp_rn(S);
-                const __half2 k64 = __float2half2_rn(kProbScale);
-                for (int i = tid; i < nvec; i += kThreads) {
-                    uint4 u = *reinterpret_cast<const uint4*>(row + 8 * i);
-                    __half2* hh = reinterpret_cast<__half2*>(&u);
-                    #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = __half22float2(hh[e]);
-                        const float e0 = __expf(f.x - M), e1 = __expf(f.y - M);
-                        // e / S, correctly rounded: one Newton step on the quotient (same result as __fdiv_rn for normal
-                        // operands, without its range checks); then fp16 (:375)
-                        float q0 = e0 * rS, q1 = e1 * rS;
-                        q0 = fmaf(fmaf(-q0, S, e0), rS, q0);
-                        q1 = fmaf(fmaf(-q1, S, e1), rS, q1);
-                        const __half2 pr = __floats2half2_rn(q0, q1);
-                        if (8 * i + 2 * e == s.T - 1) pnew[h] = __low2float(pr);
-                        if (8 * i + 2 * e + 1 == s.T - 1) pnew[h] = __high2float(pr);
-                        hh[e] = __hmul2(pr, k64);                   // exact
-                    }
-                    *reinterpret_cast<uint4*>(row + 8 * i) = u;
-                }
-            }
-            if (G > 1) __syncthreads();                             // stats are reused by the next head
-        }
-        __syncthreads();
-
-        // ================= V phase =================
-        float acc[8][4];                                            // packed part, over all of this warp's blocks
-        float zc[4] = {0.f, 0.f, 0.f, 0.f};
-        float orr[G][4];                                            // fp16 window part: lane = 4 channels
+        // ---- this range's statistics of the unit, per head: slot = index of this warp among the unit's range owners
+        const int w_first = range_owner((long long)unit * s.ipu, N, W);
         #pragma unroll
-        for (int mm = 0; mm < 8; ++mm)
-            #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
+        for (int h = 0; h < G; ++h) {
+            float m = mw[h], sm = sw[h];
+            if (h_l == h && m_blk != -INFINITY) {
+                const float mn = fmaxf(m, m_blk);
+                sm = (m == -INFINITY ? 0.f : sm * __expf(m - mn)) + s_blk * __expf(m_blk - mn);
+                m = mn;
+            }
+            float M, S;
+            warp_max_sum(m, sm, M, S);
+            if (lane == 0) p.w.stats[(int64_t)(uq0 + h) * p.w.stat_cap + (gw - w_first)] = make_float2(M, S);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// p . V  (+ softmax normalisation, output, cache update)
+// ------------------------------------------------------------------------------------------------
+
+template <int VB, int G>
+__device__ __forceinline__ void sv_issue_next(Pipe& pp, long long& cur, long long hi, const AttnParams& p, const Sched& s,
+                                              int ratio, int lane, uint64_t pol)
+{
+    const CacheDesc& c = p.c;
+    while (cur < hi && (int)(cur % s.bpu) == s.bpu - 1) ++cur;    // the new token needs no load
+    if (cur >= hi) return;
+    const int unit = (int)(cur / s.bpu), j = (int)(cur % s.bpu);
+    const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
+    if (lane == 0) {
+        uint8_t* dst = pp.prod();
+        uint64_t* bar = pp.prod_bar();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (j < s.n_vb) {
+            const uint32_t bb = (uint32_t)lay_block_bytes(VB, c.g);
+            mbar_expect_tx(bar, bb + G * kBlockTokens * 2);
+            bulk_g2s(dst, c.v_store + ((int64_t)u * c.v_cap_blocks + j) * bb, bb, bar, pol);
+            const int uq0 = u * ratio + hc * G;
+            for (int h = 0; h < G; ++h)                                   // the block's logits slices (workspace rows)
+                bulk_g2s(dst + bb + h * kBlockTokens * 2, p.w.lg + (int64_t)(uq0 + h) * p.w.ld + j * kBlockTokens,
+                         kBlockTokens * 2, bar, pol);
+        } else {
+            const int i = j - s.n_vb;
+            int slot0, nt;
+            if (i < s.vr1) { const int t0 = i * kResTile; slot0 = s.vhead + t0; nt = min(kResTile, s.seg1 - t0); }
+            else { const int t0 = (i - s.vr1) * kResTile; slot0 = t0; nt = min(kResTile, s.L - s.seg1 - t0); }
+            mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
+            bulk_g2s(dst, c.v_res + ((int64_t)u * c.v_res_cap + slot0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
+        }
+    }
+    pp.push();
+    ++cur;
+}
+
+// fp16 probability of a scaled logit: fp16(exp(x - M) / S)   (models/llama_kivi.py:375); rS = 1 / S
+__device__ __forceinline__ float prob_f32(float x, float M, float S, float rS) {
+    const float e = __expf(x - M);
+    const float q = e * rS;
+    return fmaf(fmaf(-q, S, e), rS, q);     // one Newton step on the quotient = the correctly rounded e / S
+}
+
+template <int KB, int VB, int G, int GS>
+__global__ void __launch_bounds__(kThreads, 2)
+sv_kernel(const AttnParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const CacheDesc& c = p.c;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int n_stages = kCW * p.spw;
+    uint64_t* full_all = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * p.stage_bytes);
+    uint8_t* ptr = smem + (((size_t)n_stages * (p.stage_bytes + 8) + 127) & ~(size_t)127);
+    uint8_t* scratch = ptr + warp * 128;                                     // commit_unit scratch, per warp
+
+    if (tid == 0) {
+        for (int i = 0; i < n_stages; ++i) mbar_init(&full_all[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();                                                         // the only CTA barrier: mbarrier init
+
+    const Sched s = make_sched(c);
+    const uint64_t pol = policy_evict_first();
+    const int gw = blockIdx.x * kCW + warp;
+    const long long N = (long long)p.n_units * s.bpu;                       // pseudo-blocks of the whole job
+    const long long W = min((long long)p.nw_eff, N);                        // range owners: every range is non-empty
+    if (gw >= W) return;
+    const long long lo = range_lo(gw, N, W), hi = range_lo(gw + 1, N, W);
+    const int ratio = c.H / c.Hkv;
+    Pipe pp;
+    pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
+    long long cur = lo;
+    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G>(pp, cur, hi, p, s, ratio, lane, pol);
+
+    constexpr int NG = Cols<G, GS>::NG;
+    const int h_l = t4 % G;
+    constexpr int kVBlock = Lay<VB>::kCodeBytes + 8 * NG * 4 * 16;           // bytes of a V block for (VB, GS)
+    const int rec = G * 2 * kD;                                              // floats of a partial record
+
+    long long gb = lo;
+    #pragma unroll 1
+    while (gb < hi) {
+        const int unit = (int)(gb / s.bpu);
+        const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
+        const int uq0 = u * ratio + hc * G;
+        const long long gb_end = min(hi, (long long)(unit + 1) * s.bpu);     // this warp's pseudo-blocks of this unit
+
+        // ---- (M, S) of every head of the unit from the statistics slots of the qk ranges (identical in every warp)
+        const long long Nq = (long long)p.n_units * s.ipu, Wq = min((long long)p.nw_eff, Nq);
+        const int nstat = range_owner((long long)unit * s.ipu + s.ipu - 1, Nq, Wq) - range_owner((long long)unit * s.ipu, Nq, Wq) + 1;
+        float M[G], S[G], rS[G];
+        #pragma unroll
+        for (int h = 0; h < G; ++h) {
+            const float2* st = p.w.stats + (int64_t)(uq0 + h) * p.w.stat_cap;
+            float mx = -INFINITY, sm = 0.f;
+            for (int i = lane; i < nstat; i += 32) {
+                const float2 v = __ldcg(st + i);
+                const float mn = fmaxf(mx, v.x);
+                sm = (mx == -INFINITY ? 0.f : sm * __expf(mx - mn)) + (v.x == -INFINITY ? 0.f : v.y * __expf(v.x - mn));
+                mx = mn;
+            }
+            warp_max_sum(mx, sm, M[h], S[h]);
+            rS[h] = __frcp_rn(S[h]);
+        }
+
+        // packed part: the MMA accumulators live for ONE block (mma.sync accumulates with truncation: a 100-step chain
+        // would bias the sum by ~100 * 2^-24 of its L1 mass); the lane's own outputs are then added, rounded to nearest,
+        // to running sums over this warp's blocks of the unit
+        float run[Slots<G, GS>::k];
+        float orr[G][4];                                                     // window part: lane = 4 channels
+        #pragma unroll
+        for (int e = 0; e < Slots<G, GS>::k; ++e) run[e] = 0.f;
         #pragma unroll
         for (int h = 0; h < G; ++h)
             #pragma unroll
             for (int e = 0; e < 4; ++e) orr[h][e] = 0.f;
+
         #pragma unroll 1
-        for (int a = 0; a < wp.nvb; ++a) {
-            const int blk = warp + kCW * a;
-            const int t0 = blk * kBlockTokens, nt = s.tv - t0;      // nt >= 128 except in the last block
-            pp.wait_full(m);
-            const __half* prow = lg + t0 + 2 * t4;
-            mma_block<VB, G, GS>(pp.stage(m), [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
-                const __half* pr = prow + (int64_t)h * lg_stride + 16 * cc;
-                xa = *reinterpret_cast<const uint32_t*>(pr);
-                xb = *reinterpret_cast<const uint32_t*>(pr + 8);
-                if (nt < kBlockTokens) {                            // tokens beyond the packed length belong to the window
-                    const int i0 = 16 * cc + 2 * t4;
-                    if (i0 >= nt) xa = 0u; else if (i0 + 1 >= nt) xa &= 0xFFFFu;
-                    if (i0 + 8 >= nt) xb = 0u; else if (i0 + 9 >= nt) xb &= 0xFFFFu;
+        for (; gb < gb_end; ++gb) {
+            const int j = (int)(gb - (long long)unit * s.bpu);
+            if (j < s.n_vb) {                                                // ---- packed V block (tensor cores)
+                const int t0 = j * kBlockTokens, nt = s.tv - t0;             // nt >= 128 except in the last block
+                pp.wait();
+                uint8_t* st = pp.cons();
+                __half* prob = reinterpret_cast<__half*>(st + kVBlock);      // [G][128] logits -> probabilities x 2^6
+                #pragma unroll
+                for (int h = 0; h < G; ++h) {                                // 4 tokens per lane
+                    uint2 raw = *reinterpret_cast<const uint2*>(prob + h * kBlockTokens + lane * 4);
+                    __half2* hh = reinterpret_cast<__half2*>(&raw);
+                    const __half2 k64 = __float2half2_rn(kProbScale);
+                    #pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float2 f = __half22float2(hh[e]);
+                        __half2 pr = __floats2half2_rn(prob_f32(f.x, M[h], S[h], rS[h]), prob_f32(f.y, M[h], S[h], rS[h]));
+                        const int tt = lane * 4 + 2 * e;                     // tokens beyond the packed length belong to the window
+                        if (tt >= nt) pr = __float2half2_rn(0.f);
+                        else if (tt + 1 >= nt) pr = __halves2half2(__low2half(pr), __float2half_rn(0.f));
+                        if (p.dbg_probs) {
+                            if (tt < nt) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + t0 + tt] = __low2half(pr);
+                            if (tt + 1 < nt) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + t0 + tt + 1] = __high2half(pr);
+                        }
+                        hh[e] = __hmul2(pr, k64);                            // exact
+                    }
+                    *reinterpret_cast<uint2*>(prob + h * kBlockTokens + lane * 4) = raw;
                 }
-            }, acc, zc, lane);
-            __syncwarp();
-            issue_next<KB, VB>(pp, p, s, wp, warp, lane, pol);
-            ++m;
-        }
-        #pragma unroll 1
-        for (int bq = 0; bq < wp.nvr; ++bq) {
-            const int i = wp.vr0 + kCW * bq;
-            int l0, nt;                                             // logical index of the item's first token
-            if (i < s.vr1) { l0 = i * kResTile; nt = min(kResTile, s.seg1 - l0); }
-            else { const int tt0 = (i - s.vr1) * kResTile; l0 = s.seg1 + tt0; nt = min(kResTile, s.L - s.seg1 - tt0); }
-            pp.wait_full(m);
-            const uint8_t* st = pp.stage(m);
-            #pragma unroll 2
-            for (int t = 0; t < nt; ++t) {
-                const uint2 vv = *reinterpret_cast<const uint2*>(st + t * 256 + lane * 8);
+                __syncwarp();
+                float acc[8][4];
+                float zc[4] = {0.f, 0.f, 0.f, 0.f};
+                #pragma unroll
+                for (int mm = 0; mm < 8; ++mm)
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
+                mma_block<VB, G, GS>(st, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
+                    const __half* pr = prob + h * kBlockTokens + 16 * cc + 2 * t4;
+                    xa = *reinterpret_cast<const uint32_t*>(pr);
+                    xb = *reinterpret_cast<const uint32_t*>(pr + 8);
+                }, acc, zc, lane);
+                __syncwarp();
+                pp.pop();
+                sv_issue_next<VB, G>(pp, cur, hi, p, s, ratio, lane, pol);
+                float zsel[NG];
+                gather_z<G, GS>(zc, lane, zsel);
+                finalize<VB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int, float v) { run[slot] += v; });
+            } else if (j < s.bpu - 1) {                                      // ---- fp16 V window item
+                const int i = j - s.n_vb;
+                int l0, nt;                                                  // logical index of the item's first token
+                if (i < s.vr1) { l0 = i * kResTile; nt = min(kResTile, s.seg1 - l0); }
+                else { const int tt0 = (i - s.vr1) * kResTile; l0 = s.seg1 + tt0; nt = min(kResTile, s.L - s.seg1 - tt0); }
+                // the item's probabilities: lane t < nt computes token tv + l0 + t
+                float pl[G];
+                #pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    pl[h] = 0.f;
+                    if (lane < nt) {
+                        const float x = __half2float(__ldcg(p.w.lg + (int64_t)(uq0 + h) * p.w.ld + s.tv + l0 + lane));
+                        const __half pr = __float2half_rn(prob_f32(x, M[h], S[h], rS[h]));
+                        if (p.dbg_probs) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + s.tv + l0 + lane] = pr;
+                        pl[h] = __half2float(pr);
+                    }
+                }
+                pp.wait();
+                const uint8_t* st = pp.cons();
+                #pragma unroll 2
+                for (int t = 0; t < nt; ++t) {
+                    const uint2 vv = *reinterpret_cast<const uint2*>(st + t * 256 + lane * 8);
+                    const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+                    const float2 v01 = __half22float2(vh[0]), v23 = __half22float2(vh[1]);
+                    #pragma unroll
+                    for (int h = 0; h < G; ++h) {
+                        const float pr = __shfl_sync(0xffffffffu, pl[h], t);
+                        orr[h][0] = fmaf(pr, v01.x, orr[h][0]); orr[h][1] = fmaf(pr, v01.y, orr[h][1]);
+                        orr[h][2] = fmaf(pr, v23.x, orr[h][2]); orr[h][3] = fmaf(pr, v23.y, orr[h][3]);
+                    }
+                }
+                __syncwarp();
+                pp.pop();
+                sv_issue_next<VB, G>(pp, cur, hi, p, s, ratio, lane, pol);
+            } else {                                                         // ---- the new token (v_new)
+                const uint2 vv = __ldg(reinterpret_cast<const uint2*>(p.v_new + (int64_t)u * kD) + lane);
                 const __half2* vh = reinterpret_cast<const __half2*>(&vv);
                 const float2 v01 = __half22float2(vh[0]), v23 = __half22float2(vh[1]);
                 #pragma unroll
                 for (int h = 0; h < G; ++h) {
-                    const float pr = __half2float(lg[(int64_t)h * lg_stride + s.tv + l0 + t]);   // x 2^6, undone below
+                    const float x = __half2float(__ldcg(p.w.lg + (int64_t)(uq0 + h) * p.w.ld + s.T - 1));
+                    const __half prh = __float2half_rn(prob_f32(x, M[h], S[h], rS[h]));
+                    if (p.dbg_probs && lane == 0) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + s.T - 1] = prh;
+                    const float pr = __half2float(prh);
                     orr[h][0] = fmaf(pr, v01.x, orr[h][0]); orr[h][1] = fmaf(pr, v01.y, orr[h][1]);
                     orr[h][2] = fmaf(pr, v23.x, orr[h][2]); orr[h][3] = fmaf(pr, v23.y, orr[h][3]);
                 }
             }
-            __syncwarp();
-            issue_next<KB, VB>(pp, p, s, wp, warp, lane, pol);
-            ++m;
         }
-        float zsel[NG];
-        gather_z<G, GS>(zc, lane, zsel);
-        if (!WS) __syncthreads();                                   // everyone is done reading the probabilities (red aliases them)
+
+        // ---- this warp's partial record of the unit: [G][packed | window][128]
+        const long long gb0 = (long long)unit * s.bpu;
+        const int w_first = range_owner(gb0, N, W), w_last = range_owner(gb0 + s.bpu - 1, N, W);
+        const int nparts = w_last - w_first + 1;
+        float* recp = p.w.part + ((int64_t)unit * p.w.part_cap + (gw - w_first)) * rec;
         {
-            float* rq = red + ((size_t)(warp * G + h_l) * 2 + 0) * kD;
-            finalize<VB, G, GS>(acc, zsel, lane, kProbScaleInv, [&](int o, float v) { rq[o] = v; });
+            float* rq = recp + (h_l * 2 + 0) * kD;
+            walk_slots<G, GS>(run, lane, [&](int o, float v) { rq[o] = v * kProbScaleInv; });
+            #pragma unroll
+            for (int h = 0; h < G; ++h)
+                *reinterpret_cast<float4*>(recp + (h * 2 + 1) * kD + lane * 4) = make_float4(orr[h][0], orr[h][1], orr[h][2], orr[h][3]);
+            __threadfence();
+            __syncwarp();
+        }
+        int last = 1;
+        if (nparts > 1) {
+            int old = 0;
+            if (lane == 0) old = atomicAdd(p.w.count + unit, 1);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            last = (old == nparts - 1);
+        }
+        if (last) {
+            // ---- the unit is complete: add the records in warp order, round, write the output, update the cache
+            __threadfence();
+            if (nparts > 1 && lane == 0) p.w.count[unit] = 0;
+            float qs[G][4], rs[G][4];
+            #pragma unroll
+            for (int h = 0; h < G; ++h)
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) { qs[h][e] = 0.f; rs[h][e] = 0.f; }
+            const float* r0 = p.w.part + (int64_t)unit * p.w.part_cap * rec;
+            #pragma unroll 1
+            for (int w = 0; w < nparts; ++w) {
+                #pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    const float4 a = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 0) * kD) + lane);
+                    const float4 b4 = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 1) * kD) + lane);
+                    qs[h][0] += a.x; qs[h][1] += a.y; qs[h][2] += a.z; qs[h][3] += a.w;
+                    rs[h][0] += b4.x; rs[h][1] += b4.y; rs[h][2] += b4.z; rs[h][3] += b4.w;
+                }
+            }
             #pragma unroll
             for (int h = 0; h < G; ++h) {
-                float* rr = red + ((size_t)(warp * G + h) * 2 + 1) * kD;
-                *reinterpret_cast<float4*>(rr + lane * 4) =
-                    make_float4(orr[h][0] * kProbScaleInv, orr[h][1] * kProbScaleInv, orr[h][2] * kProbScaleInv, orr[h][3] * kProbScaleInv);
+                __align__(8) __half o4[4];
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __half o = __float2half_rn(rs[h][e]);                                   // llama_kivi.py:380 / :384
+                    if (s.tv > 0) o = __hadd_rn(__float2half_rn(qs[h][e]), o);             // :382-384
+                    o4[e] = o;
+                }
+                *reinterpret_cast<uint2*>(p.out + (int64_t)(uq0 + h) * kD + lane * 4) = *reinterpret_cast<const uint2*>(o4);
             }
+            if (hc == 0) commit_unit<KB, VB>(p, s, u, lane, scratch);
         }
-        __syncthreads();
-        for (int i = tid; i < G * kD; i += kThreads) {
-            const int h = i / kD, d = i % kD;
-            float q_sum = 0.f, r_sum = 0.f;
-            #pragma unroll
-            for (int w = 0; w < kCW; ++w) {
-                q_sum += red[((size_t)(w * G + h) * 2 + 0) * kD + d];
-                r_sum += red[((size_t)(w * G + h) * 2 + 1) * kD + d];
-            }
-            r_sum = fmaf(pnew[h], __half2float(p.v_new[(int64_t)u * kD + d]), r_sum);
-            __half o = __float2half_rn(r_sum);                                          // llama_kivi.py:380 / :384
-            if (s.tv > 0) o = __hadd_rn(__float2half_rn(q_sum), o);                     // :382-384
-            p.out[(int64_t)(uq0 + h) * kD + d] = o;
-        }
-        if (hc == 0) commit_unit<KB, VB>(p, s, u, tid, scratch, reinterpret_cast<uint8_t*>(red));
-        __syncthreads();                                            // q2 / qlin / lg / red are reused by the next unit
     }
 }
 
@@ -724,34 +949,50 @@ attention_kernel(const AttnParams p)
 // ------------------------------------------------------------------------------------------------
 static int g_num_sms = 0, g_max_smem = 0;
 
-template <int KB, int VB, int G, int GS>
-static int launch_attention(AttnParams& p, int max_kv_len, cudaStream_t st)
-{
-    const CacheDesc& c = p.c;
+static inline void query_device() {
     if (g_num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
-    int stage = max(lay_block_bytes(KB, c.g), lay_block_bytes(VB, c.g));
+}
+
+// workspace carve-up (shared by kivi_decode_workspace_bytes and the launcher)
+static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, int max_kv_len, void* base, Workspace* w)
+{
+    query_device();
+    const int64_t rows = (int64_t)c.B * c.H;
+    const int64_t ld = ((int64_t)max_kv_len + 16 + 127) / 128 * 128 + 128;
+    const int bpu_max = cdiv(max_kv_len, kBlockTokens) + cdiv(c.R + 1, kResTile) + 4;
+    const int warps = g_num_sms * 2 * kCW;
+    const int part_cap = min(bpu_max, cdiv(warps, n_units) + 2);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { const int64_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const int64_t o_lg = take(rows * ld * 2);
+    const int stat_cap = part_cap;                                          // one slot per qk range of a unit
+    const int64_t o_st = take(rows * stat_cap * 8);
+    const int64_t o_pt = take((int64_t)n_units * part_cap * G * 2 * kD * 4);
+    const int64_t o_ct = take((int64_t)n_units * 4);
+    if (w) {
+        uint8_t* b = (uint8_t*)base;
+        w->lg = (__half*)(b + o_lg); w->ld = ld;
+        w->stats = (float2*)(b + o_st); w->stat_cap = stat_cap;
+        w->part = (float*)(b + o_pt); w->part_cap = part_cap;
+        w->count = (int*)(b + o_ct);
+    }
+    return off;
+}
+
+template <int KB, int VB, int G, int GS>
+static int launch_attention(AttnParams& p, cudaStream_t st)
+{
+    const CacheDesc& c = p.c;
+    query_device();
+    int stage = max(lay_block_bytes(KB, c.g), lay_block_bytes(VB, c.g) + G * kBlockTokens * 2);
     stage = max(stage, kResBytes);
     p.stage_bytes = (stage + 127) / 128 * 128;
-    const int red_bytes = kCW * G * 2 * kD * 4;
-    const int base = 512 /*barriers, alignment*/ + G * 32 * 8 + G * kD * 4 + 128 + kScratchBytes;
-    // logits rows in shared memory when they fit next to >= 2 stages per warp, else in the caller's workspace
-    const int t_need = (max_kv_len + 8 + 63) / 64 * 64;
-    p.t_cap = max(red_bytes / (2 * G), t_need);
-    int fixed = base + G * p.t_cap * 2;
-    p.use_ws = 0;
-    const bool force_ws = p.ws && getenv("KIVI_FORCE_WORKSPACE");       // tests: exercise the workspace path at small sizes
-    if (force_ws || (g_max_smem - fixed) / (kCW * p.stage_bytes) < 2) {
-        if (!p.ws) return KIVI_ERR_CAPACITY;
-        if (p.ld < max_kv_len + 8) return KIVI_ERR_CAPACITY;
-        p.use_ws = 1;
-        p.t_cap = red_bytes / (2 * G);
-        fixed = base + red_bytes;
-    }
+    const int fixed = 512 + max(kCW * G * (32 * 8 + kD * 4), kCW * 128);     // barriers + per-warp q buffers / commit scratch
     int ctas = 2;
     p.spw = min(4, (g_max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
     if (p.spw < 2) {
@@ -760,28 +1001,38 @@ static int launch_attention(AttnParams& p, int max_kv_len, cudaStream_t st)
     }
     if (p.spw < 1) return KIVI_ERR_CAPACITY;
     const size_t smem = (size_t)kCW * p.spw * p.stage_bytes + fixed;
+    auto kqk = qk_kernel<KB, G, GS>;
+    auto ksv = sv_kernel<KB, VB, G, GS>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel<KB, VB, G, GS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attention_kernel<KB, VB, G, GS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+        cudaError_t e = cudaFuncSetAttribute(kqk, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ksv, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int grid = min(p.n_units, g_num_sms * ctas);
-    if (p.use_ws) attention_kernel<KB, VB, G, GS, true><<<grid, kThreads, smem, st>>>(p);
-    else          attention_kernel<KB, VB, G, GS, false><<<grid, kThreads, smem, st>>>(p);
+    const int grid = g_num_sms * ctas;
+    // sv range owners: never more warps than pseudo-blocks (bpu >= 1 per unit), never more partial records per unit than
+    // the workspace holds
+    p.nw_eff = min(grid * kCW, p.n_units);                                   // >= 1 pseudo-block per warp for any state
+    {
+        // more parallelism when units are few and long: up to part_cap - 2 warps per unit
+        const long long want = (long long)p.n_units * max(1, p.w.part_cap - 2);
+        p.nw_eff = (int)min((long long)grid * kCW, max((long long)p.nw_eff, want));
+    }
+    kqk<<<grid, kThreads, smem, st>>>(p);
+    int rc = post_launch(); if (rc) return rc;
+    ksv<<<grid, kThreads, smem, st>>>(p);
     return post_launch();
 }
 
 template <int KB, int VB>
-static int dispatch_attention(AttnParams& p, int G, int max_kv_len, cudaStream_t st)
+static int dispatch_attention(AttnParams& p, int G, cudaStream_t st)
 {
     #define KIVI_GS(GS_)                                                                  \
         if (p.c.g == GS_) {                                                               \
-            if (G == 4) return launch_attention<KB, VB, 4, GS_>(p, max_kv_len, st);       \
-            if (G == 2) return launch_attention<KB, VB, 2, GS_>(p, max_kv_len, st);       \
-            return launch_attention<KB, VB, 1, GS_>(p, max_kv_len, st);                   \
+            if (G == 4) return launch_attention<KB, VB, 4, GS_>(p, st);                   \
+            if (G == 2) return launch_attention<KB, VB, 2, GS_>(p, st);                   \
+            return launch_attention<KB, VB, 1, GS_>(p, st);                               \
         }
     KIVI_GS(32)
     KIVI_GS(64)

@@ -1,5 +1,8 @@
-// instantiation of the fused decode attention kernel for k_bits = 2, v_bits = 4 (all G, all group sizes)
+// instantiation of the decode attention kernels for k_bits = 2, v_bits = 4 (all G, all group sizes)
 #include "kivi_attn.cuh"
 namespace kivi {
-int attention_k2v4(AttnParams& p, int G, int max_kv_len, cudaStream_t st) { return dispatch_attention<2, 4>(p, G, max_kv_len, st); }
+int attention_k2v4(AttnParams& p, int G, cudaStream_t st) { return dispatch_attention<2, 4>(p, G, st); }
+int64_t workspace_k2v4(const CacheDesc& c, int n_units, int G, int max_kv_len, void* base, Workspace* w) {
+    return carve_workspace(c, n_units, G, max_kv_len, base, w);
+}
 }

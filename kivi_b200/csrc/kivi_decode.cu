@@ -1,43 +1,55 @@
-// kivi_decode.cu -- C-ABI entry of the fused decode attention; the kernel lives in kivi_attn.cuh and is
-// instantiated per (k_bits, v_bits) pair in kivi_attn_k{2,4}v{2,4}.cu (compiled in parallel).
+// kivi_decode.cu -- C-ABI entry of the decode attention; the kernels live in kivi_attn.cuh and are instantiated
+// per (k_bits, v_bits) pair in kivi_attn_k{2,4}v{2,4}.cu (compiled in parallel).
 #include <cstdlib>
 #include "kivi_attn.cuh"
 
 namespace kivi {
-int attention_k2v2(AttnParams& p, int G, int max_kv_len, cudaStream_t st);
-int attention_k4v4(AttnParams& p, int G, int max_kv_len, cudaStream_t st);
-int attention_k2v4(AttnParams& p, int G, int max_kv_len, cudaStream_t st);
-int attention_k4v2(AttnParams& p, int G, int max_kv_len, cudaStream_t st);
+int attention_k2v2(AttnParams& p, int G, cudaStream_t st);
+int attention_k4v4(AttnParams& p, int G, cudaStream_t st);
+int attention_k2v4(AttnParams& p, int G, cudaStream_t st);
+int attention_k4v2(AttnParams& p, int G, cudaStream_t st);
 }
 
 using namespace kivi;
 
+static int gqa_chunk(int ratio) {
+    int G = ratio % 4 == 0 ? 4 : (ratio % 2 == 0 ? 2 : 1);
+    if (const char* e = getenv("KIVI_GQA_G")) { const int g = atoi(e); if ((g == 1 || g == 2 || g == 4) && ratio % g == 0) G = g; }
+    return G;
+}
+
+extern "C" int64_t kivi_decode_workspace_bytes(const kivi_cache_t* cache, int max_kv_len)
+{
+    CacheDesc c;
+    int rc = make_desc(cache, &c);
+    if (rc) return rc;
+    if (max_kv_len <= 0) return KIVI_ERR_SHAPE;
+    const int ratio = c.H / c.Hkv, G = gqa_chunk(ratio);
+    return carve_workspace(c, c.B * c.Hkv * (ratio / G), G, max_kv_len, nullptr, nullptr);
+}
+
 extern "C" int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const void* k_new, const void* v_new,
-                                         const void* mask, void* out, void* workspace, int64_t ld,
+                                         const void* mask, void* out, void* workspace, int64_t workspace_bytes,
                                          void* dbg_logits, void* dbg_probs, int64_t dbg_stride, int max_kv_len, void* stream)
 {
     AttnParams p;
     int rc = make_desc(cache, &p.c);
     if (rc) return rc;
-    if (!q || !k_new || !v_new || !out) return KIVI_ERR_NULL;
+    if (!q || !k_new || !v_new || !out || !workspace) return KIVI_ERR_NULL;
     if (max_kv_len <= 0) return KIVI_ERR_SHAPE;
     if (max_kv_len > p.c.k_cap_blocks * kBlockTokens) return KIVI_ERR_CAPACITY;
-    if (workspace) {
-        if (ld <= 0 || ld % 8 != 0) return KIVI_ERR_ALIGN;
-        if (reinterpret_cast<uintptr_t>(workspace) % 16 != 0) return KIVI_ERR_ALIGN;
-    }
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return KIVI_ERR_ALIGN;
     p.q = (const __half*)q; p.k_new = (const __half*)k_new; p.v_new = (const __half*)v_new; p.mask = (const __half*)mask;
     p.out = (__half*)out; p.dbg_logits = (__half*)dbg_logits; p.dbg_probs = (__half*)dbg_probs; p.dbg_stride = dbg_stride;
-    p.ws = (__half*)workspace; p.ld = ld;
     const int ratio = p.c.H / p.c.Hkv;
-    int G = ratio % 4 == 0 ? 4 : (ratio % 2 == 0 ? 2 : 1);
-    if (const char* e = getenv("KIVI_GQA_G")) { const int g = atoi(e); if ((g == 1 || g == 2 || g == 4) && ratio % g == 0) G = g; }
+    const int G = gqa_chunk(ratio);
     p.hchunks = ratio / G;
     p.n_units = p.c.B * p.c.Hkv * p.hchunks;
+    if (carve_workspace(p.c, p.n_units, G, max_kv_len, workspace, &p.w) > workspace_bytes) return KIVI_ERR_CAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
-    if (p.c.k_bits == 2 && p.c.v_bits == 2) return attention_k2v2(p, G, max_kv_len, st);
-    if (p.c.k_bits == 4 && p.c.v_bits == 4) return attention_k4v4(p, G, max_kv_len, st);
-    if (p.c.k_bits == 2 && p.c.v_bits == 4) return attention_k2v4(p, G, max_kv_len, st);
-    if (p.c.k_bits == 4 && p.c.v_bits == 2) return attention_k4v2(p, G, max_kv_len, st);
+    if (p.c.k_bits == 2 && p.c.v_bits == 2) return attention_k2v2(p, G, st);
+    if (p.c.k_bits == 4 && p.c.v_bits == 4) return attention_k4v4(p, G, st);
+    if (p.c.k_bits == 2 && p.c.v_bits == 4) return attention_k2v4(p, G, st);
+    if (p.c.k_bits == 4 && p.c.v_bits == 2) return attention_k4v2(p, G, st);
     return KIVI_ERR_BITS;
 }

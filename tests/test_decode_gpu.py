@@ -34,21 +34,18 @@ def _tuple_equal(got, exp):
             np.testing.assert_array_equal(a, b, err_msg=f"tuple[{i}]")
 
 
-def _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=1024, n_layers=1, mode="smem"):
-    """mode "smem": logits rows in shared memory; "workspace": forced into the global workspace (the long-context path)."""
+def _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=1024, n_layers=1, mode=None):
     from kivi_b200.cache import KiviCache
-    c = KiviCache(n_layers, B, H, Hkv, 128, kb, vb, g, R, max_tokens)
-    if mode == "workspace":
-        c._alloc_ws()
-    return c
+    return KiviCache(n_layers, B, H, Hkv, 128, kb, vb, g, R, max_tokens)
 
 
-@pytest.fixture(params=["smem", "workspace"])
+@pytest.fixture(params=["G-auto", "G-1"])
 def mode(request, monkeypatch):
-    if request.param == "workspace":
-        monkeypatch.setenv("KIVI_FORCE_WORKSPACE", "1")
+    """G-auto: the query heads of a KV head share the MMAs (chunks of up to 4); G-1: one head per unit."""
+    if request.param == "G-1":
+        monkeypatch.setenv("KIVI_GQA_G", "1")
     else:
-        monkeypatch.delenv("KIVI_FORCE_WORKSPACE", raising=False)
+        monkeypatch.delenv("KIVI_GQA_G", raising=False)
     return request.param
 
 
