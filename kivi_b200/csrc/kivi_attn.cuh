@@ -7,9 +7,9 @@
 // outputs -> fp16 add).
 //
 // Execution model: EVERY WARP IS AN AUTONOMOUS WORKER -- no CTA barrier anywhere, no per-unit tail.
-//   qk_kernel   items (dealt round-robin over all warps of the persistent grid): one 128-token packed K block,
-//               <= 24 tokens of the fp16 K window, or the new token.  An item writes its scaled fp16 logits to the
-//               workspace row and its softmax statistics (max, sum exp) to the row's statistics slots.
+//   qk_kernel   the (unit, pseudo-block) sequence [K blocks | fp16 K window items | new token] of all units is cut
+//               into one contiguous range per warp.  A warp writes the scaled fp16 logits of its pseudo-blocks to the
+//               workspace row and ONE (max, sum exp) statistics pair per unit it touches (online softmax per lane).
 //   sv_kernel   the (unit, pseudo-block) sequence [V blocks | fp16 V window items | new token] of all units is cut
 //               into one contiguous range per warp.  A warp combines the row's statistics into (M, S) -- the same
 //               instructions on the same data in every warp, hence bit-identical -- turns the logits slice of its
@@ -44,7 +44,13 @@ int make_desc(const kivi_cache_t* k, CacheDesc* d);
 
 constexpr int kCW = 8;                 // warps per CTA (they never synchronise with each other)
 constexpr int kThreads = kCW * 32;
-constexpr int kResTile = 24;           // tokens per fp16-window item (24 * 256 B = 6 KB)
+// A pipeline stage holds kHalfChunks of the 8 chunks (16 inner indices each) of a packed block: 8 = whole blocks
+// (one 6 KB bulk copy), 4 = half blocks.  Measured (tools/sweep_occupancy.sh, profiles/): half blocks allow 3 CTAs
+// per SM (24 warps) but cost +25 % instructions and more, smaller copies -> 175 us vs 140 us per cfg-2 layer.
+constexpr int kHalfChunks = 8;
+constexpr int kParts = 8 / kHalfChunks;     // stage-items per packed block
+constexpr int kPartTokens = 16 * kHalfChunks;   // inner indices (V: tokens) per stage-item
+constexpr int kResTile = 3 * kHalfChunks;   // tokens per fp16-window item (256 B each): the size of a stage
 constexpr int kResBytes = kResTile * kD * 2;
 constexpr float kRcpSqrtD = 1.0f / 11.313708f;   // ATen: x * (1.0f / float(math.sqrt(128)))  (llama_kivi.py:339)
 // probabilities are kept x 2^6 while they feed the MMAs: exact, and it keeps the fp16 residual fma(p, s, -hi) of
@@ -109,6 +115,13 @@ __device__ __forceinline__ __half scale_logit(float acc) {
     return __float2half_rn(__half2float(__float2half_rn(acc)) * kRcpSqrtD);
 }
 
+// exp(x) = ex2.approx(x * log2 e), results below 2^-126 flushed to zero: two instructions (__expf adds a range fix-up)
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t h2_as_u32(const __half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u32_as_h2(const uint32_t u) { return *reinterpret_cast<const __half2*>(&u); }
 
@@ -135,16 +148,16 @@ struct Cols {
 };
 
 // ------------------------------------------------------------------------------------------------
-// One packed block (128 inner x 128 outer) on the tensor cores.
-//   st      : the block in shared memory (codes, then meta)
+// Half a packed block (inner indices 16*c0 .. 16*c0+63, 128 outer) on the tensor cores.
+//   st      : the half block in shared memory: 4 chunks of codes, then the 4 chunks of meta
 //   getx    : (chunk c, head h, &xa, &xb) -> the lane's x values (half2) of inner indices 16c+2t+{0,1} and
-//             16c+2t+{8,9} for head h
+//             16c+2t+{8,9} for head h (c = chunk within the whole block)
 //   acc[mm] : accumulators of MMA mm (outer rows 16mm .. 16mm+15): lane (g8, t) holds rows g8 / g8+8 of
 //             columns 2t, 2t+1 = (group-in-fragment t / G, head t % G, hi | lo)
 //   zc      : zero-term accumulator: row g8 = group min(g8 >> 1, NG-1), columns 2t, 2t+1 = head t % G
 // ------------------------------------------------------------------------------------------------
 template <int BITS, int G, int GS, class XF>
-__device__ __forceinline__ void mma_block(const uint8_t* st, XF&& getx, float (&acc)[8][4], float (&zc)[4], int lane)
+__device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, float (&acc)[8][4], float (&zc)[4], int lane)
 {
     using L = Lay<BITS>;
     using CL = Cols<G, GS>;
@@ -154,14 +167,14 @@ __device__ __forceinline__ void mma_block(const uint8_t* st, XF&& getx, float (&
     const int gi = g8 / (2 * G);                        // group-in-fragment of this lane's B column
     const int gz = min(g8 >> 1, NG - 1);                // group of this lane's A rows in the zero-term MMA
     const __half2 msel = (g8 & 1) ? __float2half2_rn(-1.f) : __float2half2_rn(0.f);
-    const uint8_t* meta = st + L::kCodeBytes + t * 16;
+    const uint8_t* meta = st + kHalfChunks * L::kChunkBytes + t * 16;
     constexpr uint32_t kField = ((1u << BITS) - 1u) * 0x00010001u;
     #pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
+    for (int cl = 0; cl < kHalfChunks; ++cl) {
         uint32_t xa, xb;
-        getx(c, hb, xa, xb);
+        getx(c0 + cl, hb, xa, xb);
         // {z(2t,2t+1), s(2t,2t+1), z(2t+8,2t+9), s(2t+8,2t+9)} of group gz: as is, the A operand of the zero-term MMA
-        const uint4 mz = *reinterpret_cast<const uint4*>(meta + (c * NG + gz) * 64);
+        const uint4 mz = *reinterpret_cast<const uint4*>(meta + (cl * NG + gz) * 64);
         mma_16816(zc, mz.x, mz.y, mz.z, mz.w, xa, xb);
         uint32_t b0[NF], b1[NF];
         if (G == 1 && NF == 1) {                        // the B column's group is gz
@@ -170,13 +183,13 @@ __device__ __forceinline__ void mma_block(const uint8_t* st, XF&& getx, float (&
             #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const int grp = min(f * GPF + gi, NG - 1);
-                const uint4 ms = *reinterpret_cast<const uint4*>(meta + (c * NG + grp) * 64);
+                const uint4 ms = *reinterpret_cast<const uint4*>(meta + (cl * NG + grp) * 64);
                 b0[f] = b_prep(xa, ms.y, msel); b1[f] = b_prep(xb, ms.w, msel);
             }
         }
         #pragma unroll
         for (int sl = 0; sl < L::kSlabs; ++sl) {
-            const uint4 w4 = *reinterpret_cast<const uint4*>(st + (c * L::kSlabs + sl) * 512 + lane * 16);
+            const uint4 w4 = *reinterpret_cast<const uint4*>(st + (cl * L::kSlabs + sl) * 512 + lane * 16);
             const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
             uint32_t wl4[4], wr4[4], wr6[4], wr8[4];    // the shifted copies a bit width needs (the others fold away)
             #pragma unroll
@@ -206,6 +219,16 @@ __device__ __forceinline__ void gather_z(const float (&zc)[4], int lane, float (
         zsel[grp] = __shfl_sync(0xffffffffu, zc[0], 8 * grp + (lane & 3));
 }
 
+// branch-free v[t] for t = (t2, t1): three SELP (the compiler turns long ?: chains over registers into branches)
+__device__ __forceinline__ float selp(float a, float b, bool p) {
+    float r;
+    asm("{ .reg .pred q; setp.ne.b32 q, %3, 0; selp.f32 %0, %2, %1, q; }" : "=f"(r) : "f"(a), "f"(b), "r"((int)p));
+    return r;
+}
+__device__ __forceinline__ float sel4(float v0, float v1, float v2, float v3, bool t1, bool t2) {
+    return selp(selp(v0, v1, t1), selp(v2, v3, t1), t2);
+}
+
 // Hand every (slot, outer row, value) this lane owns to `emit`: value = ((hi + lo) * 2^(24-P) + Z) * post for its
 // head t % G; `slot` is a compile-time index (< kSlots) of the value within the lane.  Lane (g8, t) owns rows
 // g8 / g8+8 of the MMAs whose group-in-fragment is t / G.
@@ -219,15 +242,16 @@ __device__ __forceinline__ void finalize(const float (&acc)[8][4], const float (
     const int g8 = lane >> 2, t = lane & 3;
     if (G == 1 && GS == 32) {
         // lane t owns MMAs 2t and 2t+1 (group t): pick them with selects instead of 8 predicated copies of the tail
+        const bool t1 = t & 1, t2 = t & 2;
         float lo[4], hi[4];
         #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            lo[e] = t == 0 ? acc[0][e] : t == 1 ? acc[2][e] : t == 2 ? acc[4][e] : acc[6][e];
-            hi[e] = t == 0 ? acc[1][e] : t == 1 ? acc[3][e] : t == 2 ? acc[5][e] : acc[7][e];
+            lo[e] = sel4(acc[0][e], acc[2][e], acc[4][e], acc[6][e], t1, t2);
+            hi[e] = sel4(acc[1][e], acc[3][e], acc[5][e], acc[7][e], t1, t2);
         }
-        const float sl = (t == 0 ? inv_pos_scale<BITS>(0) : t == 1 ? inv_pos_scale<BITS>(2) : t == 2 ? inv_pos_scale<BITS>(4) : inv_pos_scale<BITS>(6)) * post;
-        const float sh = (t == 0 ? inv_pos_scale<BITS>(1) : t == 1 ? inv_pos_scale<BITS>(3) : t == 2 ? inv_pos_scale<BITS>(5) : inv_pos_scale<BITS>(7)) * post;
-        const float zt = (t == 0 ? zsel[0] : t == 1 ? zsel[1] : t == 2 ? zsel[2] : zsel[3]) * post;
+        const float sl = sel4(inv_pos_scale<BITS>(0), inv_pos_scale<BITS>(2), inv_pos_scale<BITS>(4), inv_pos_scale<BITS>(6), t1, t2) * post;
+        const float sh = sel4(inv_pos_scale<BITS>(1), inv_pos_scale<BITS>(3), inv_pos_scale<BITS>(5), inv_pos_scale<BITS>(7), t1, t2) * post;
+        const float zt = sel4(zsel[0], zsel[1], zsel[2], zsel[3], t1, t2) * post;
         const int o = 32 * t + g8;
         emit(0, o, fmaf(lo[0] + lo[1], sl, zt));
         emit(1, o + 8, fmaf(lo[2] + lo[3], sl, zt));
@@ -381,7 +405,7 @@ __device__ __forceinline__ void warp_max_sum(float mx, float sm, float& M, float
     for (int o = 16; o >= 1; o >>= 1) {
         const float mo = __shfl_xor_sync(0xffffffffu, mx, o), so = __shfl_xor_sync(0xffffffffu, sm, o);
         const float mn = fmaxf(mx, mo);
-        sm = (mx == -INFINITY ? 0.f : sm * __expf(mx - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
+        sm = (mx == -INFINITY ? 0.f : sm * fast_exp(mx - mn)) + (mo == -INFINITY ? 0.f : so * fast_exp(mo - mn));
         mx = mn;
     }
     M = mx; S = sm;
@@ -399,8 +423,18 @@ __device__ __forceinline__ __half apply_mask(__half v, const __half* mask, int64
 // contiguous range per warp: warp w of the W range owners handles [lo(w), lo(w+1)), lo(w) = floor(w * N / W).
 // W <= N, so every range is non-empty and a unit of L pseudo-blocks meets at most ceil(L * W / N) + 1 ranges.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long range_lo(long long w, long long N, long long W) { return w * N / W; }
-__device__ __forceinline__ int range_owner(long long gb, long long N, long long W) { return (int)(((gb + 1) * W - 1) / N); }
+struct Ranges {                         // N pseudo-blocks over W owners; 32-bit arithmetic whenever (N + 1) * W fits
+    unsigned N, W; bool small;
+    __device__ __forceinline__ Ranges(long long n, long long w) : N((unsigned)n), W((unsigned)w), small((n + 1) * w < (1ll << 32)) {}
+    __device__ __forceinline__ int lo(int w) const { return small ? (int)((unsigned)w * N / W) : (int)((long long)w * N / W); }
+    __device__ __forceinline__ int owner(int gb) const {
+        return small ? (int)((((unsigned)gb + 1u) * W - 1u) / N) : (int)((((long long)gb + 1) * W - 1) / N);
+    }
+};
+
+struct Cursor {                         // (unit, pseudo-block, half) position of a warp in its range
+    int unit, j, half, left;            // left = pseudo-blocks remaining in the range (including j)
+};
 
 // online softmax statistics: fold the values x[0..n) (any of them may be -inf = "no value") into (m, s)
 template <int N_>
@@ -408,45 +442,57 @@ __device__ __forceinline__ void fold_stats(float& m, float& s, const float (&x)[
     float mn = m;
     #pragma unroll
     for (int e = 0; e < N_; ++e) mn = fmaxf(mn, x[e]);
-    if (mn == -INFINITY) return;
-    float acc = s * __expf(m - mn);                     // m == -inf -> s * 0
-    #pragma unroll
-    for (int e = 0; e < N_; ++e) acc += __expf(x[e] - mn);
-    m = mn; s = acc;
+    if (mn != -INFINITY) {
+        float acc = s * fast_exp(m - mn);                 // m == -inf -> s * 0
+        #pragma unroll
+        for (int e = 0; e < N_; ++e) acc += fast_exp(x[e] - mn);
+        m = mn; s = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // q . K^T  (+ scale, mask, per-range softmax statistics)
 // ------------------------------------------------------------------------------------------------
 template <int KB>
-__device__ __forceinline__ void qk_issue_next(Pipe& pp, long long& cur, long long hi, const AttnParams& p, const Sched& s,
+__device__ __forceinline__ void qk_issue_next(Pipe& pp, Cursor& cur, const AttnParams& p, const Sched& s,
                                               int lane, uint64_t pol)
 {
     const CacheDesc& c = p.c;
-    while (cur < hi && (int)(cur % s.ipu) == s.ipu - 1) ++cur;    // the new token needs no load
-    if (cur >= hi) return;
-    const int unit = (int)(cur / s.ipu), j = (int)(cur % s.ipu);
-    const int u = p.hchunks == 1 ? unit : unit / p.hchunks;
+    if (cur.left > 0 && cur.j == s.ipu - 1) {                     // the new token needs no load
+        cur.j = 0; ++cur.unit; --cur.left;
+    }
+    if (cur.left <= 0) return;
     if (lane == 0) {
+        const int u = p.hchunks == 1 ? cur.unit : cur.unit / p.hchunks;
         uint8_t* dst = pp.prod();
         uint64_t* bar = pp.prod_bar();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (j < s.n_kb) {
-            const uint32_t bb = (uint32_t)lay_block_bytes(KB, c.g);
-            mbar_expect_tx(bar, bb);
-            bulk_g2s(dst, c.k_store + ((int64_t)u * c.k_cap_blocks + j) * bb, bb, bar, pol);
+        if (cur.j < s.n_kb) {
+            constexpr int cb = kHalfChunks * Lay<KB>::kChunkBytes;    // codes of a stage-item
+            const int mb = lay_meta_bytes(c.g) / kParts;
+            const uint8_t* blk = c.k_store + ((int64_t)u * c.k_cap_blocks + cur.j) * lay_block_bytes(KB, c.g);
+            mbar_expect_tx(bar, (uint32_t)(cb + mb));
+            if (kParts == 1) {
+                bulk_g2s(dst, blk, (uint32_t)(cb + mb), bar, pol);    // codes and meta are contiguous: one copy
+            } else {
+                bulk_g2s(dst, blk + cur.half * cb, cb, bar, pol);
+                bulk_g2s(dst + cb, blk + kParts * cb + cur.half * mb, (uint32_t)mb, bar, pol);
+            }
         } else {
-            const int t0 = (j - s.n_kb) * kResTile, nt = min(kResTile, s.r - t0);
+            const int t0 = (cur.j - s.n_kb) * kResTile, nt = min(kResTile, s.r - t0);
             mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
             bulk_g2s(dst, c.k_res + ((int64_t)u * c.R + t0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
         }
     }
     pp.push();
-    ++cur;
+    if (cur.j < s.n_kb && cur.half + 1 < kParts) { ++cur.half; return; }
+    cur.half = 0;
+    --cur.left;
+    if (++cur.j == s.ipu) { cur.j = 0; ++cur.unit; }
 }
 
 template <int KB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (G == 1 && kParts > 1) ? 3 : 2)
 qk_kernel(const AttnParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -471,41 +517,52 @@ qk_kernel(const AttnParams p)
     const long long N = (long long)p.n_units * s.ipu;                        // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);
     if (gw >= W) return;
-    const long long lo = range_lo(gw, N, W), hi = range_lo(gw + 1, N, W);
+    const Ranges rg(N, W);
+    const int lo = rg.lo(gw), hi = rg.lo(gw + 1);
     Pipe pp;
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
-    long long cur = lo;
-    for (int i = 0; i < p.spw; ++i) qk_issue_next<KB>(pp, cur, hi, p, s, lane, pol);
+    Cursor cur;
+    cur.unit = lo / s.ipu; cur.j = lo - cur.unit * s.ipu; cur.half = 0; cur.left = hi - lo;
+    for (int i = 0; i < p.spw; ++i) qk_issue_next<KB>(pp, cur, p, s, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
     const int ratio = c.H / c.Hkv;
     const int h_l = t4 % G;
     const bool slow = p.mask || p.dbg_logits;                                // mask / debug copies: rare, off the fast path
 
-    long long gb = lo;
+    int unit = lo / s.ipu, j = lo - unit * s.ipu, left = hi - lo;
+    // q of a unit, fetched one unit ahead (registers): lane = (chunk, t) of the B-fragment pairs / 4 channels of the fp32 copy
+    uint2 qf[G], ql[G];
+    auto fetch_q = [&](int un) {
+        const int u_ = p.hchunks == 1 ? un : un / p.hchunks, hc_ = p.hchunks == 1 ? 0 : un % p.hchunks;
+        const int row0 = u_ * ratio + hc_ * G;
+        #pragma unroll
+        for (int h = 0; h < G; ++h) {
+            const uint32_t* qh = reinterpret_cast<const uint32_t*>(p.q + (int64_t)(row0 + h) * kD + 16 * (lane >> 2) + 2 * (lane & 3));
+            qf[h] = make_uint2(__ldg(qh), __ldg(qh + 4));
+            ql[h] = __ldg(reinterpret_cast<const uint2*>(p.q + (int64_t)(row0 + h) * kD) + lane);
+        }
+    };
+    fetch_q(unit);
     #pragma unroll 1
-    while (gb < hi) {
-        const int unit = (int)(gb / s.ipu);
+    while (left > 0) {
         const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
         const int b = u / c.Hkv;
         const int uq0 = u * ratio + hc * G;
-        const long long gb_end = min(hi, (long long)(unit + 1) * s.ipu);     // this warp's pseudo-blocks of this unit
+        const int j_first = j;
+        const int n_here = min(left, s.ipu - j);                             // this warp's pseudo-blocks of this unit
 
         // ---- this warp's copy of q: half2 pairs in B-fragment order, fp32 in channel order
         __syncwarp();
-        for (int i = lane; i < G * 32; i += 32) {
-            const int h = i >> 5, cc = (i >> 2) & 7, tt = i & 3;
-            const uint32_t* qh = reinterpret_cast<const uint32_t*>(p.q + (int64_t)(uq0 + h) * kD + 16 * cc + 2 * tt);
-            q2[i] = make_uint2(__ldg(qh), __ldg(qh + 4));
-        }
         #pragma unroll
         for (int h = 0; h < G; ++h) {
-            const uint2 qv = __ldg(reinterpret_cast<const uint2*>(p.q + (int64_t)(uq0 + h) * kD) + lane);
-            const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+            q2[h * 32 + lane] = qf[h];
+            const __half2* qh = reinterpret_cast<const __half2*>(&ql[h]);
             const float2 a = __half22float2(qh[0]), b2 = __half22float2(qh[1]);
             *reinterpret_cast<float4*>(qlin + h * kD + lane * 4) = make_float4(a.x, a.y, b2.x, b2.y);
         }
         __syncwarp();
+        if (left > n_here) fetch_q(unit + 1);                                // the range continues into the next unit
 
         // lane-local online softmax statistics: (m_blk, s_blk) over the packed-block logits of head h_l held by this lane,
         // (mw[h], sw[h]) over the window / new-token logits this lane wrote for head h
@@ -515,8 +572,7 @@ qk_kernel(const AttnParams p)
         for (int h = 0; h < G; ++h) { mw[h] = -INFINITY; sw[h] = 0.f; }
 
         #pragma unroll 1
-        for (; gb < gb_end; ++gb) {
-            const int j = (int)(gb - (long long)unit * s.ipu);
+        for (int k = 0; k < n_here; ++k, ++j) {
             if (j < s.n_kb) {                                                // ---- packed K block (tensor cores)
                 float acc[8][4];
                 float zc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -524,14 +580,17 @@ qk_kernel(const AttnParams p)
                 for (int mm = 0; mm < 8; ++mm)
                     #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
-                pp.wait();
-                mma_block<KB, G, GS>(pp.cons(), [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
-                    const uint2 v = q2[(h * 8 + cc) * 4 + t4];
-                    xa = v.x; xb = v.y;
-                }, acc, zc, lane);
-                __syncwarp();
-                pp.pop();
-                qk_issue_next<KB>(pp, cur, hi, p, s, lane, pol);
+                #pragma unroll 1
+                for (int half = 0; half < kParts; ++half) {
+                    pp.wait();
+                    mma_half<KB, G, GS>(pp.cons(), half * kHalfChunks, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
+                        const uint2 v = q2[(h * 8 + cc) * 4 + t4];
+                        xa = v.x; xb = v.y;
+                    }, acc, zc, lane);
+                    __syncwarp();
+                    pp.pop();
+                    qk_issue_next<KB>(pp, cur, p, s, lane, pol);
+                }
                 float zsel[NG];
                 gather_z<G, GS>(zc, lane, zsel);
                 const int64_t rowi = uq0 + h_l;
@@ -554,9 +613,9 @@ qk_kernel(const AttnParams p)
                             mx = fmaxf(mx, __half2float(hv));
                         });
                         if (mx != -INFINITY) {
-                            float a2 = s_blk * __expf(m_blk - mx);
+                            float a2 = s_blk * fast_exp(m_blk - mx);
                             finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
-                                a2 += __expf(__half2float(scale_logit(v)) - mx);
+                                a2 += fast_exp(__half2float(scale_logit(v)) - mx);
                             });
                             m_blk = mx; s_blk = a2;
                         }
@@ -577,9 +636,9 @@ qk_kernel(const AttnParams p)
                         }
                     });
                     if (mx != -INFINITY) {
-                        float a2 = s_blk * __expf(m_blk - mx);
+                        float a2 = s_blk * fast_exp(m_blk - mx);
                         finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
-                            if (o < nvalid) a2 += __expf(__half2float(logit_of(o, v)) - mx);
+                            if (o < nvalid) a2 += fast_exp(__half2float(logit_of(o, v)) - mx);
                         });
                         m_blk = mx; s_blk = a2;
                     }
@@ -630,7 +689,7 @@ qk_kernel(const AttnParams p)
                 }
                 __syncwarp();
                 pp.pop();
-                qk_issue_next<KB>(pp, cur, hi, p, s, lane, pol);
+                qk_issue_next<KB>(pp, cur, p, s, lane, pol);
             } else {                                                         // ---- the new token
                 const uint2 kv = __ldg(reinterpret_cast<const uint2*>(p.k_new + (int64_t)u * kD) + lane);
                 const __half2* kh = reinterpret_cast<const __half2*>(&kv);
@@ -655,49 +714,60 @@ qk_kernel(const AttnParams p)
         }
 
         // ---- this range's statistics of the unit, per head: slot = index of this warp among the unit's range owners
-        const int w_first = range_owner((long long)unit * s.ipu, N, W);
+        const int w_first = rg.owner(unit * s.ipu);
         #pragma unroll
         for (int h = 0; h < G; ++h) {
             float m = mw[h], sm = sw[h];
             if (h_l == h && m_blk != -INFINITY) {
                 const float mn = fmaxf(m, m_blk);
-                sm = (m == -INFINITY ? 0.f : sm * __expf(m - mn)) + s_blk * __expf(m_blk - mn);
+                sm = (m == -INFINITY ? 0.f : sm * fast_exp(m - mn)) + s_blk * fast_exp(m_blk - mn);
                 m = mn;
             }
             float M, S;
             warp_max_sum(m, sm, M, S);
             if (lane == 0) p.w.stats[(int64_t)(uq0 + h) * p.w.stat_cap + (gw - w_first)] = make_float2(M, S);
         }
+        (void)j_first;
+        left -= n_here;
+        if (j == s.ipu) { j = 0; ++unit; }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // p . V  (+ softmax normalisation, output, cache update)
 // ------------------------------------------------------------------------------------------------
-
 template <int VB, int G>
-__device__ __forceinline__ void sv_issue_next(Pipe& pp, long long& cur, long long hi, const AttnParams& p, const Sched& s,
+__device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnParams& p, const Sched& s,
                                               int ratio, int lane, uint64_t pol)
 {
     const CacheDesc& c = p.c;
-    while (cur < hi && (int)(cur % s.bpu) == s.bpu - 1) ++cur;    // the new token needs no load
-    if (cur >= hi) return;
-    const int unit = (int)(cur / s.bpu), j = (int)(cur % s.bpu);
-    const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
+    if (cur.left > 0 && cur.j == s.bpu - 1) {                     // the new token needs no load
+        cur.j = 0; ++cur.unit; --cur.left;
+    }
+    if (cur.left <= 0) return;
     if (lane == 0) {
+        const int u = p.hchunks == 1 ? cur.unit : cur.unit / p.hchunks, hc = p.hchunks == 1 ? 0 : cur.unit % p.hchunks;
         uint8_t* dst = pp.prod();
         uint64_t* bar = pp.prod_bar();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (j < s.n_vb) {
-            const uint32_t bb = (uint32_t)lay_block_bytes(VB, c.g);
-            mbar_expect_tx(bar, bb + G * kBlockTokens * 2);
-            bulk_g2s(dst, c.v_store + ((int64_t)u * c.v_cap_blocks + j) * bb, bb, bar, pol);
+        if (cur.j < s.n_vb) {
+            constexpr int cb = kHalfChunks * Lay<VB>::kChunkBytes;    // codes of a stage-item
+            const int mb = lay_meta_bytes(c.g) / kParts;
+            const uint8_t* blk = c.v_store + ((int64_t)u * c.v_cap_blocks + cur.j) * lay_block_bytes(VB, c.g);
+            mbar_expect_tx(bar, (uint32_t)(cb + mb + G * kPartTokens * 2));
+            if (kParts == 1) {
+                bulk_g2s(dst, blk, (uint32_t)(cb + mb), bar, pol);    // codes and meta are contiguous: one copy
+            } else {
+                bulk_g2s(dst, blk + cur.half * cb, cb, bar, pol);
+                bulk_g2s(dst + cb, blk + kParts * cb + cur.half * mb, (uint32_t)mb, bar, pol);
+            }
             const int uq0 = u * ratio + hc * G;
-            for (int h = 0; h < G; ++h)                                   // the block's logits slices (workspace rows)
-                bulk_g2s(dst + bb + h * kBlockTokens * 2, p.w.lg + (int64_t)(uq0 + h) * p.w.ld + j * kBlockTokens,
-                         kBlockTokens * 2, bar, pol);
+            for (int h = 0; h < G; ++h)                               // the logits of the item's tokens (workspace rows)
+                bulk_g2s(dst + cb + mb + h * kPartTokens * 2,
+                         p.w.lg + (int64_t)(uq0 + h) * p.w.ld + cur.j * kBlockTokens + cur.half * kPartTokens,
+                         kPartTokens * 2, bar, pol);
         } else {
-            const int i = j - s.n_vb;
+            const int i = cur.j - s.n_vb;
             int slot0, nt;
             if (i < s.vr1) { const int t0 = i * kResTile; slot0 = s.vhead + t0; nt = min(kResTile, s.seg1 - t0); }
             else { const int t0 = (i - s.vr1) * kResTile; slot0 = t0; nt = min(kResTile, s.L - s.seg1 - t0); }
@@ -706,24 +776,27 @@ __device__ __forceinline__ void sv_issue_next(Pipe& pp, long long& cur, long lon
         }
     }
     pp.push();
-    ++cur;
+    if (cur.j < s.n_vb && cur.half + 1 < kParts) { ++cur.half; return; }
+    cur.half = 0;
+    --cur.left;
+    if (++cur.j == s.bpu) { cur.j = 0; ++cur.unit; }
 }
 
 // fp16 probability of a scaled logit: fp16(exp(x - M) / S)   (models/llama_kivi.py:375); rS = 1 / S
 __device__ __forceinline__ float prob_f32(float x, float M, float S, float rS) {
-    const float e = __expf(x - M);
+    const float e = fast_exp(x - M);
     const float q = e * rS;
     return fmaf(fmaf(-q, S, e), rS, q);     // one Newton step on the quotient = the correctly rounded e / S
 }
 
 template <int KB, int VB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (G == 1 && kParts > 1) ? 3 : 2)
 sv_kernel(const AttnParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const CacheDesc& c = p.c;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g8 = lane >> 2, t4 = lane & 3;
+    const int t4 = lane & 3;
     const int n_stages = kCW * p.spw;
     uint64_t* full_all = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * p.stage_bytes);
     uint8_t* ptr = smem + (((size_t)n_stages * (p.stage_bytes + 8) + 127) & ~(size_t)127);
@@ -741,43 +814,60 @@ sv_kernel(const AttnParams p)
     const long long N = (long long)p.n_units * s.bpu;                       // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);                        // range owners: every range is non-empty
     if (gw >= W) return;
-    const long long lo = range_lo(gw, N, W), hi = range_lo(gw + 1, N, W);
+    const Ranges rg(N, W);
+    const int lo = rg.lo(gw), hi = rg.lo(gw + 1);
     const int ratio = c.H / c.Hkv;
     Pipe pp;
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
-    long long cur = lo;
-    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G>(pp, cur, hi, p, s, ratio, lane, pol);
+    Cursor cur;
+    cur.unit = lo / s.bpu; cur.j = lo - cur.unit * s.bpu; cur.half = 0; cur.left = hi - lo;
+    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
     const int h_l = t4 % G;
-    constexpr int kVBlock = Lay<VB>::kCodeBytes + 8 * NG * 4 * 16;           // bytes of a V block for (VB, GS)
+    constexpr int kHalfBytes = kHalfChunks * Lay<VB>::kChunkBytes + kHalfChunks * NG * 64;   // codes + meta of half a V block
     const int rec = G * 2 * kD;                                              // floats of a partial record
+    const long long Nq = (long long)p.n_units * s.ipu;
+    const Ranges rq(Nq, min((long long)p.nw_eff, Nq));                      // the qk kernel's ranges
 
-    long long gb = lo;
+    int unit = lo / s.bpu, j = lo - unit * s.bpu, left = hi - lo;
+    // statistics slots of a unit, fetched one unit ahead: lane i holds slot i of every head
+    float2 sn[G];
+    int nstat = 0;
+    auto fetch_stats = [&](int un) {
+        const int u_ = p.hchunks == 1 ? un : un / p.hchunks, hc_ = p.hchunks == 1 ? 0 : un % p.hchunks;
+        const int row0 = u_ * ratio + hc_ * G;
+        nstat = rq.owner(un * s.ipu + s.ipu - 1) - rq.owner(un * s.ipu) + 1;
+        #pragma unroll
+        for (int h = 0; h < G; ++h) {
+            sn[h] = make_float2(-INFINITY, 0.f);
+            if (lane < nstat) sn[h] = __ldcg(p.w.stats + (int64_t)(row0 + h) * p.w.stat_cap + lane);
+        }
+    };
+    fetch_stats(unit);
     #pragma unroll 1
-    while (gb < hi) {
-        const int unit = (int)(gb / s.bpu);
+    while (left > 0) {
         const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
         const int uq0 = u * ratio + hc * G;
-        const long long gb_end = min(hi, (long long)(unit + 1) * s.bpu);     // this warp's pseudo-blocks of this unit
+        const int n_here = min(left, s.bpu - j);                             // this warp's pseudo-blocks of this unit
 
-        // ---- (M, S) of every head of the unit from the statistics slots of the qk ranges (identical in every warp)
-        const long long Nq = (long long)p.n_units * s.ipu, Wq = min((long long)p.nw_eff, Nq);
-        const int nstat = range_owner((long long)unit * s.ipu + s.ipu - 1, Nq, Wq) - range_owner((long long)unit * s.ipu, Nq, Wq) + 1;
+        // ---- (M, S) of every head of the unit from the statistics slots of the qk ranges (identical in every warp);
+        // the slots were fetched one unit ahead
         float M[G], S[G], rS[G];
         #pragma unroll
         for (int h = 0; h < G; ++h) {
+            float mx = sn[h].x, sm = sn[h].y;
             const float2* st = p.w.stats + (int64_t)(uq0 + h) * p.w.stat_cap;
-            float mx = -INFINITY, sm = 0.f;
-            for (int i = lane; i < nstat; i += 32) {
+            for (int i = lane + 32; i < nstat; i += 32) {                    // more than 32 ranges on one unit: few, long units
                 const float2 v = __ldcg(st + i);
                 const float mn = fmaxf(mx, v.x);
-                sm = (mx == -INFINITY ? 0.f : sm * __expf(mx - mn)) + (v.x == -INFINITY ? 0.f : v.y * __expf(v.x - mn));
+                sm = (mx == -INFINITY ? 0.f : sm * fast_exp(mx - mn)) + (v.x == -INFINITY ? 0.f : v.y * fast_exp(v.x - mn));
                 mx = mn;
             }
             warp_max_sum(mx, sm, M[h], S[h]);
             rS[h] = __frcp_rn(S[h]);
         }
+        if (left > n_here) fetch_stats(unit + 1);                            // the range continues into the next unit
 
         // packed part: the MMA accumulators live for ONE block (mma.sync accumulates with truncation: a 100-step chain
         // would bias the sum by ~100 * 2^-24 of its L1 mass); the lane's own outputs are then added, rounded to nearest,
@@ -792,48 +882,46 @@ sv_kernel(const AttnParams p)
             for (int e = 0; e < 4; ++e) orr[h][e] = 0.f;
 
         #pragma unroll 1
-        for (; gb < gb_end; ++gb) {
-            const int j = (int)(gb - (long long)unit * s.bpu);
+        for (int k = 0; k < n_here; ++k, ++j) {
             if (j < s.n_vb) {                                                // ---- packed V block (tensor cores)
-                const int t0 = j * kBlockTokens, nt = s.tv - t0;             // nt >= 128 except in the last block
-                pp.wait();
-                uint8_t* st = pp.cons();
-                __half* prob = reinterpret_cast<__half*>(st + kVBlock);      // [G][128] logits -> probabilities x 2^6
-                #pragma unroll
-                for (int h = 0; h < G; ++h) {                                // 4 tokens per lane
-                    uint2 raw = *reinterpret_cast<const uint2*>(prob + h * kBlockTokens + lane * 4);
-                    __half2* hh = reinterpret_cast<__half2*>(&raw);
-                    const __half2 k64 = __float2half2_rn(kProbScale);
-                    #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float2 f = __half22float2(hh[e]);
-                        __half2 pr = __floats2half2_rn(prob_f32(f.x, M[h], S[h], rS[h]), prob_f32(f.y, M[h], S[h], rS[h]));
-                        const int tt = lane * 4 + 2 * e;                     // tokens beyond the packed length belong to the window
-                        if (tt >= nt) pr = __float2half2_rn(0.f);
-                        else if (tt + 1 >= nt) pr = __halves2half2(__low2half(pr), __float2half_rn(0.f));
-                        if (p.dbg_probs) {
-                            if (tt < nt) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + t0 + tt] = __low2half(pr);
-                            if (tt + 1 < nt) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + t0 + tt + 1] = __high2half(pr);
-                        }
-                        hh[e] = __hmul2(pr, k64);                            // exact
-                    }
-                    *reinterpret_cast<uint2*>(prob + h * kBlockTokens + lane * 4) = raw;
-                }
-                __syncwarp();
                 float acc[8][4];
                 float zc[4] = {0.f, 0.f, 0.f, 0.f};
                 #pragma unroll
                 for (int mm = 0; mm < 8; ++mm)
                     #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
-                mma_block<VB, G, GS>(st, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
-                    const __half* pr = prob + h * kBlockTokens + 16 * cc + 2 * t4;
-                    xa = *reinterpret_cast<const uint32_t*>(pr);
-                    xb = *reinterpret_cast<const uint32_t*>(pr + 8);
-                }, acc, zc, lane);
-                __syncwarp();
-                pp.pop();
-                sv_issue_next<VB, G>(pp, cur, hi, p, s, ratio, lane, pol);
+                #pragma unroll 1
+                for (int half = 0; half < kParts; ++half) {
+                    const int t0 = j * kBlockTokens + half * kPartTokens, nt = s.tv - t0;   // nt >= kPartTokens except at the end of the store
+                    pp.wait();
+                    uint8_t* st = pp.cons();
+                    __half* prob = reinterpret_cast<__half*>(st + kHalfBytes);   // [G][kPartTokens] logits -> probabilities x 2^6
+                    #pragma unroll
+                    for (int h = 0; h < G; ++h) {
+                        #pragma unroll
+                        for (int e = 0; e < kPartTokens / 64; ++e) {         // 2 tokens per lane and pass
+                            const int tt = (e * 32 + lane) * 2;
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(prob + h * kPartTokens + tt));
+                            __half2 pr = __floats2half2_rn(prob_f32(f.x, M[h], S[h], rS[h]), prob_f32(f.y, M[h], S[h], rS[h]));
+                            if (tt >= nt) pr = __float2half2_rn(0.f);        // tokens beyond the packed length belong to the window
+                            else if (tt + 1 >= nt) pr = __halves2half2(__low2half(pr), __float2half_rn(0.f));
+                            if (p.dbg_probs) {
+                                if (tt < nt) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + t0 + tt] = __low2half(pr);
+                                if (tt + 1 < nt) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + t0 + tt + 1] = __high2half(pr);
+                            }
+                            *reinterpret_cast<__half2*>(prob + h * kPartTokens + tt) = __hmul2(pr, __float2half2_rn(kProbScale));   // exact
+                        }
+                    }
+                    __syncwarp();
+                    mma_half<VB, G, GS>(st, half * kHalfChunks, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
+                        const __half* pr = prob + h * kPartTokens + 16 * (cc - half * kHalfChunks) + 2 * t4;
+                        xa = *reinterpret_cast<const uint32_t*>(pr);
+                        xb = *reinterpret_cast<const uint32_t*>(pr + 8);
+                    }, acc, zc, lane);
+                    __syncwarp();
+                    pp.pop();
+                    sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
+                }
                 float zsel[NG];
                 gather_z<G, GS>(zc, lane, zsel);
                 finalize<VB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int, float v) { run[slot] += v; });
@@ -870,7 +958,7 @@ sv_kernel(const AttnParams p)
                 }
                 __syncwarp();
                 pp.pop();
-                sv_issue_next<VB, G>(pp, cur, hi, p, s, ratio, lane, pol);
+                sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
             } else {                                                         // ---- the new token (v_new)
                 const uint2 vv = __ldg(reinterpret_cast<const uint2*>(p.v_new + (int64_t)u * kD) + lane);
                 const __half2* vh = reinterpret_cast<const __half2*>(&vv);
@@ -888,8 +976,8 @@ sv_kernel(const AttnParams p)
         }
 
         // ---- this warp's partial record of the unit: [G][packed | window][128]
-        const long long gb0 = (long long)unit * s.bpu;
-        const int w_first = range_owner(gb0, N, W), w_last = range_owner(gb0 + s.bpu - 1, N, W);
+        const int gb0 = unit * s.bpu;
+        const int w_first = rg.owner(gb0), w_last = rg.owner(gb0 + s.bpu - 1);
         const int nparts = w_last - w_first + 1;
         float* recp = p.w.part + ((int64_t)unit * p.w.part_cap + (gw - w_first)) * rec;
         {
@@ -941,6 +1029,8 @@ sv_kernel(const AttnParams p)
             }
             if (hc == 0) commit_unit<KB, VB>(p, s, u, lane, scratch);
         }
+        left -= n_here;
+        if (j == s.bpu) { j = 0; ++unit; }
     }
 }
 
@@ -958,6 +1048,8 @@ static inline void query_device() {
     }
 }
 
+constexpr int kMaxCtasPerSm = kParts == 1 ? 2 : 3;
+
 // workspace carve-up (shared by kivi_decode_workspace_bytes and the launcher)
 static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, int max_kv_len, void* base, Workspace* w)
 {
@@ -965,7 +1057,7 @@ static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, in
     const int64_t rows = (int64_t)c.B * c.H;
     const int64_t ld = ((int64_t)max_kv_len + 16 + 127) / 128 * 128 + 128;
     const int bpu_max = cdiv(max_kv_len, kBlockTokens) + cdiv(c.R + 1, kResTile) + 4;
-    const int warps = g_num_sms * 2 * kCW;
+    const int warps = g_num_sms * kMaxCtasPerSm * kCW;
     const int part_cap = min(bpu_max, cdiv(warps, n_units) + 2);
     int64_t off = 0;
     auto take = [&](int64_t bytes) { const int64_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -989,16 +1081,23 @@ static int launch_attention(AttnParams& p, cudaStream_t st)
 {
     const CacheDesc& c = p.c;
     query_device();
-    int stage = max(lay_block_bytes(KB, c.g), lay_block_bytes(VB, c.g) + G * kBlockTokens * 2);
-    stage = max(stage, kResBytes);
+    const int half_k = kHalfChunks * Lay<KB>::kChunkBytes + lay_meta_bytes(c.g) / kParts;
+    const int half_v = kHalfChunks * Lay<VB>::kChunkBytes + lay_meta_bytes(c.g) / kParts + G * kPartTokens * 2;
+    const int stage = max(max(half_k, half_v), kResBytes);
     p.stage_bytes = (stage + 127) / 128 * 128;
     const int fixed = 512 + max(kCW * G * (32 * 8 + kD * 4), kCW * 128);     // barriers + per-warp q buffers / commit scratch
-    int ctas = 2;
-    p.spw = min(4, (g_max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
-    if (p.spw < 2) {
-        ctas = 1;
-        p.spw = min(4, (g_max_smem - fixed) / (kCW * p.stage_bytes));
+    int ctas = G == 1 ? kMaxCtasPerSm : 2;                                   // the kernels' __launch_bounds__
+    p.spw = 0;
+    for (; ctas >= 1; --ctas) {                                              // most CTAs per SM that still get >= 2 stages per warp
+        p.spw = min(4, (g_max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
+        if (p.spw >= 2) break;
     }
+    if (ctas < 1) { ctas = 1; p.spw = (g_max_smem - fixed) / (kCW * p.stage_bytes); }
+    if (const char* e = getenv("KIVI_CTAS_PER_SM")) {                        // tuning knobs (tools/microbench.py)
+        const int v = atoi(e);
+        if (v >= 1 && v <= ctas) { ctas = v; p.spw = min(8, (g_max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes)); }
+    }
+    if (const char* e = getenv("KIVI_STAGES_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= p.spw) p.spw = v; }
     if (p.spw < 1) return KIVI_ERR_CAPACITY;
     const size_t smem = (size_t)kCW * p.spw * p.stage_bytes + fixed;
     auto kqk = qk_kernel<KB, G, GS>;
@@ -1011,14 +1110,10 @@ static int launch_attention(AttnParams& p, cudaStream_t st)
         attr_set = true;
     }
     const int grid = g_num_sms * ctas;
-    // sv range owners: never more warps than pseudo-blocks (bpu >= 1 per unit), never more partial records per unit than
-    // the workspace holds
-    p.nw_eff = min(grid * kCW, p.n_units);                                   // >= 1 pseudo-block per warp for any state
-    {
-        // more parallelism when units are few and long: up to part_cap - 2 warps per unit
-        const long long want = (long long)p.n_units * max(1, p.w.part_cap - 2);
-        p.nw_eff = (int)min((long long)grid * kCW, max((long long)p.nw_eff, want));
-    }
+    // range owners: at least one pseudo-block each (the kernels clamp to the number of pseudo-blocks), and never more
+    // ranges per unit than the workspace has record / statistics slots: part_cap - 2 warps per unit at most
+    const long long want = (long long)p.n_units * max(1, p.w.part_cap - 2);
+    p.nw_eff = (int)min((long long)grid * kCW, want);
     kqk<<<grid, kThreads, smem, st>>>(p);
     int rc = post_launch(); if (rc) return rc;
     ksv<<<grid, kThreads, smem, st>>>(p);
