@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libkivi_b200.so")
+SO_PATH = os.environ.get("KIVI_B200_LIB") or os.path.join(_HERE, "csrc", "libkivi_b200.so")   # override: tuning builds
 _LIB = None
 
 _i32, _i64, _vp = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p

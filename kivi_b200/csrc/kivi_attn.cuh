@@ -38,6 +38,15 @@
 #include <cstdlib>
 #include "kivi_decode.cuh"
 
+// tuning knobs of the chunk loop (tools/build_variants.py measures the alternatives)
+#ifndef KIVI_UNROLL
+#define KIVI_UNROLL 4
+#endif
+constexpr int kChunkUnroll = KIVI_UNROLL;
+#ifndef KIVI_SHIFT_IMAD
+#define KIVI_SHIFT_IMAD 0
+#endif
+
 namespace kivi {
 
 int make_desc(const kivi_cache_t* k, CacheDesc* d);
@@ -169,7 +178,7 @@ __device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, f
     const __half2 msel = (g8 & 1) ? __float2half2_rn(-1.f) : __float2half2_rn(0.f);
     const uint8_t* meta = st + kHalfChunks * L::kChunkBytes + t * 16;
     constexpr uint32_t kField = ((1u << BITS) - 1u) * 0x00010001u;
-    #pragma unroll 2
+    #pragma unroll (kChunkUnroll)
     for (int cl = 0; cl < kHalfChunks; ++cl) {
         uint32_t xa, xb;
         getx(c0 + cl, hb, xa, xb);
@@ -193,7 +202,13 @@ __device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, f
             const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
             uint32_t wl4[4], wr4[4], wr6[4], wr8[4];    // the shifted copies a bit width needs (the others fold away)
             #pragma unroll
-            for (int r = 0; r < 4; ++r) { wl4[r] = w[r] << 4; wr4[r] = w[r] >> 4; wr6[r] = w[r] >> 6; wr8[r] = w[r] >> 8; }
+            for (int r = 0; r < 4; ++r) {                 // right shifts as IMAD.HI: the FMA pipe has room, the ALU pipe (LOP3) does not
+#if KIVI_SHIFT_IMAD
+                wl4[r] = w[r] << 4; wr4[r] = __umulhi(w[r], 1u << 28); wr6[r] = __umulhi(w[r], 1u << 26); wr8[r] = __umulhi(w[r], 1u << 24);
+#else
+                wl4[r] = w[r] << 4; wr4[r] = w[r] >> 4; wr6[r] = w[r] >> 6; wr8[r] = w[r] >> 8;
+#endif
+            }
             #pragma unroll
             for (int j = 0; j < L::F; ++j) {
                 uint32_t a[4];
@@ -845,6 +860,42 @@ sv_kernel(const AttnParams p)
         }
     };
     fetch_stats(unit);
+    int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
+    // The last warp to arrive for a unit adds the records in range order, rounds, writes the output, updates the cache.
+    auto finish_unit = [&](int un, int nparts) {
+        const int u = p.hchunks == 1 ? un : un / p.hchunks, hc = p.hchunks == 1 ? 0 : un % p.hchunks;
+        const int uq0 = u * ratio + hc * G;
+        __threadfence();                                                     // acquire the other warps' records
+        if (nparts > 1 && lane == 0) p.w.count[un] = 0;
+        float qs[G][4], rs[G][4];
+        #pragma unroll
+        for (int h = 0; h < G; ++h)
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) { qs[h][e] = 0.f; rs[h][e] = 0.f; }
+        const float* r0 = p.w.part + (int64_t)un * p.w.part_cap * rec;
+        #pragma unroll 1
+        for (int w = 0; w < nparts; ++w) {
+            #pragma unroll
+            for (int h = 0; h < G; ++h) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 0) * kD) + lane);
+                const float4 b4 = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 1) * kD) + lane);
+                qs[h][0] += a.x; qs[h][1] += a.y; qs[h][2] += a.z; qs[h][3] += a.w;
+                rs[h][0] += b4.x; rs[h][1] += b4.y; rs[h][2] += b4.z; rs[h][3] += b4.w;
+            }
+        }
+        #pragma unroll
+        for (int h = 0; h < G; ++h) {
+            __align__(8) __half o4[4];
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                __half o = __float2half_rn(rs[h][e]);                                   // llama_kivi.py:380 / :384
+                if (s.tv > 0) o = __hadd_rn(__float2half_rn(qs[h][e]), o);             // :382-384
+                o4[e] = o;
+            }
+            *reinterpret_cast<uint2*>(p.out + (int64_t)(uq0 + h) * kD + lane * 4) = *reinterpret_cast<const uint2*>(o4);
+        }
+        if (hc == 0) commit_unit<KB, VB>(p, s, u, lane, scratch);
+    };
     #pragma unroll 1
     while (left > 0) {
         const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
@@ -986,52 +1037,24 @@ sv_kernel(const AttnParams p)
             #pragma unroll
             for (int h = 0; h < G; ++h)
                 *reinterpret_cast<float4*>(recp + (h * 2 + 1) * kD + lane * 4) = make_float4(orr[h][0], orr[h][1], orr[h][2], orr[h][3]);
-            __threadfence();
-            __syncwarp();
         }
-        int last = 1;
+        // the arrival of the PREVIOUS unit has had a whole unit's time to return: finalise it if this warp was its last
+        if (pend_unit >= 0 && __shfl_sync(0xffffffffu, pend_old, 0) == pend_nparts - 1) finish_unit(pend_unit, pend_nparts);
+        pend_unit = -1;
+        // arrive: the records of all lanes happen-before lane 0's release (__syncwarp); the counter's old value is not
+        // needed before the next unit is done, so its round trip to L2 is off the critical path
+        __syncwarp();
         if (nparts > 1) {
-            int old = 0;
-            if (lane == 0) old = atomicAdd(p.w.count + unit, 1);
-            old = __shfl_sync(0xffffffffu, old, 0);
-            last = (old == nparts - 1);
-        }
-        if (last) {
-            // ---- the unit is complete: add the records in warp order, round, write the output, update the cache
-            __threadfence();
-            if (nparts > 1 && lane == 0) p.w.count[unit] = 0;
-            float qs[G][4], rs[G][4];
-            #pragma unroll
-            for (int h = 0; h < G; ++h)
-                #pragma unroll
-                for (int e = 0; e < 4; ++e) { qs[h][e] = 0.f; rs[h][e] = 0.f; }
-            const float* r0 = p.w.part + (int64_t)unit * p.w.part_cap * rec;
-            #pragma unroll 1
-            for (int w = 0; w < nparts; ++w) {
-                #pragma unroll
-                for (int h = 0; h < G; ++h) {
-                    const float4 a = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 0) * kD) + lane);
-                    const float4 b4 = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 1) * kD) + lane);
-                    qs[h][0] += a.x; qs[h][1] += a.y; qs[h][2] += a.z; qs[h][3] += a.w;
-                    rs[h][0] += b4.x; rs[h][1] += b4.y; rs[h][2] += b4.z; rs[h][3] += b4.w;
-                }
-            }
-            #pragma unroll
-            for (int h = 0; h < G; ++h) {
-                __align__(8) __half o4[4];
-                #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    __half o = __float2half_rn(rs[h][e]);                                   // llama_kivi.py:380 / :384
-                    if (s.tv > 0) o = __hadd_rn(__float2half_rn(qs[h][e]), o);             // :382-384
-                    o4[e] = o;
-                }
-                *reinterpret_cast<uint2*>(p.out + (int64_t)(uq0 + h) * kD + lane * 4) = *reinterpret_cast<const uint2*>(o4);
-            }
-            if (hc == 0) commit_unit<KB, VB>(p, s, u, lane, scratch);
+            if (lane == 0)
+                asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + unit) : "memory");
+            pend_unit = unit; pend_nparts = nparts;
+        } else {
+            finish_unit(unit, 1);                                            // the whole unit was this warp's
         }
         left -= n_here;
         if (j == s.bpu) { j = 0; ++unit; }
     }
+    if (pend_unit >= 0 && __shfl_sync(0xffffffffu, pend_old, 0) == pend_nparts - 1) finish_unit(pend_unit, pend_nparts);
 }
 
 // ------------------------------------------------------------------------------------------------
