@@ -59,12 +59,18 @@ constexpr int kThreads = kCW * 32;
 constexpr int kHalfChunks = 8;
 constexpr int kParts = 8 / kHalfChunks;     // stage-items per packed block
 constexpr int kPartTokens = 16 * kHalfChunks;   // inner indices (V: tokens) per stage-item
-constexpr int kResTile = 3 * kHalfChunks;   // tokens per fp16-window item (256 B each): the size of a stage
+constexpr int kResTile = 16;                // tokens per fp16-window item (256 B each): one MMA tile of tokens
 constexpr int kResBytes = kResTile * kD * 2;
 constexpr float kRcpSqrtD = 1.0f / 11.313708f;   // ATen: x * (1.0f / float(math.sqrt(128)))  (llama_kivi.py:339)
 // probabilities are kept x 2^6 while they feed the MMAs: exact, and it keeps the fp16 residual fma(p, s, -hi) of
 // small probabilities out of the denormal range
 constexpr float kProbScale = 64.f, kProbScaleInv = 1.f / 64.f;
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start while its
+// predecessor in the stream is still draining; pdl_wait() blocks until the predecessor has completed and flushed, and
+// pdl_trigger() tells the runtime that the successor may start launching.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 
 struct Workspace {                     // carved from the caller's buffer (kivi_decode_workspace_bytes)
     __half* lg; long long ld;          // [B*H][ld] scaled logits (fp16), ld % 128 == 0
@@ -323,18 +329,22 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
 {
     const CacheDesc& c = p.c;
     const int g = c.g;
+    // every input is loaded up front: the loads are independent, and under load a dependent global round trip costs ~2 us
+    uint4 vnew4 = make_uint4(0u, 0u, 0u, 0u), knew4 = make_uint4(0u, 0u, 0u, 0u);
+    uint2 vold = make_uint2(0u, 0u);
+    if (lane < kD / 8) vnew4 = __ldg(reinterpret_cast<const uint4*>(p.v_new + (int64_t)u * kD) + lane);
+    if (lane >= 16) knew4 = __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (lane - 16));
+    if (s.L + 1 > c.R) vold = __ldcg(reinterpret_cast<const uint2*>(c.v_res + (int64_t)u * c.v_res_cap * kD + win_off(s.vhead, lane * 4)));
     // ---- V: v_new joins the ring; if the window would exceed R, its oldest token is quantised per token
-    if (lane < kD / 8)
-        reinterpret_cast<uint4*>(c.v_res + ((int64_t)u * c.v_res_cap + (s.vhead + s.L) % c.v_res_cap) * kD)[lane] =
-            __ldg(reinterpret_cast<const uint4*>(p.v_new + (int64_t)u * kD) + lane);
+    if (lane < kD / 8)                                                                  // window rows are unit-swizzled (win_unit)
+        reinterpret_cast<uint4*>(c.v_res + (int64_t)u * c.v_res_cap * kD)[win_unit((s.vhead + s.L) % c.v_res_cap, lane)] = vnew4;
     if (s.L + 1 > c.R) {
         constexpr int F = 16 / VB, kSlabRows = 16 * F, kSlabs = 128 / kSlabRows;
         const float maxq = (float)((1 << VB) - 1);
-        const __half* src = c.v_res + ((int64_t)u * c.v_res_cap + s.vhead) * kD;
         const int bb = lay_block_bytes(VB, g);
         uint8_t* blk = c.v_store + ((int64_t)u * c.v_cap_blocks + s.tv / kBlockTokens) * bb;
         const int inner = s.tv % kBlockTokens;
-        const uint2 raw = *reinterpret_cast<const uint2*>(src + lane * 4);              // 4 channels per lane
+        const uint2 raw = vold;                                                         // 4 channels per lane
         const __half2* rh = reinterpret_cast<const __half2*>(&raw);
         const float2 x01 = __half22float2(rh[0]), x23 = __half22float2(rh[1]);
         const float x[4] = {x01.x, x01.y, x23.x, x23.y};
@@ -368,46 +378,74 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
     }
     // ---- K: k_new joins the window, or completes it -> quantise the R tokens per channel
     if (s.r + 1 < c.R) {
-        if (lane >= 16)
-            reinterpret_cast<uint4*>(c.k_res + ((int64_t)u * c.R + s.r) * kD)[lane - 16] =
-                __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (lane - 16));
+        if (lane >= 16) reinterpret_cast<uint4*>(c.k_res + (int64_t)u * c.R * kD)[win_unit(s.r, lane - 16)] = knew4;
     } else {
-        // once per R steps.  A lane owns channels d = lane + 32 i; per (channel, group of g tokens): min / max, then
-        // chunks of 16 consecutive tokens = one field position j in the 16 half-words (row = token % 16) of (d, slab).
-        constexpr int F = 16 / KB, kSlabRows = 16 * F;
+        // once per R steps.  A lane owns channels d = lane + 32 i.  Per channel the 16 * kSlabs half-words (row = token % 16 of
+        // a slab) of the destination block are assembled in registers: per group of g tokens, 32 values at a time (independent
+        // loads), min / max, then each chunk of 16 consecutive tokens fills ONE field position j of the 16 half-words.
+        constexpr int F = 16 / KB, kSlabRows = 16 * F, kSlabs = 128 / kSlabRows;
         const float maxq = (float)((1 << KB) - 1);
         const int bb = lay_block_bytes(KB, g);
         uint8_t* ub = c.k_store + (int64_t)u * c.k_cap_blocks * bb;
         const __half* win = c.k_res + (int64_t)u * c.R * kD;
         const __half* knew = p.k_new + (int64_t)u * kD;
-        auto tokval = [&](int t, int d) -> float {
-            return __half2float(t < c.R - 1 ? win[(int64_t)t * kD + d] : knew[d]);
-        };
+        const int nblk = max(1, c.R / kBlockTokens);                                    // R in {32, 64, 128, 256}
+        const int cnt = min(c.R, kBlockTokens);                                         // flushed tokens per destination block
         #pragma unroll 1
-        for (int d = lane; d < kD; d += 32) {
+        for (int bi = 0; bi < nblk; ++bi) {
+            const int tb = s.tk + bi * kBlockTokens;                                    // first flushed token of this block
+            const int o0 = tb % kBlockTokens;                                           // its outer index (multiple of R)
+            uint8_t* blk = ub + (int64_t)(tb / kBlockTokens) * bb;
             #pragma unroll 1
-            for (int grp = 0; grp < c.R / g; ++grp) {
-                float mnf = tokval(grp * g, d), mxf = mnf;
-                #pragma unroll 4
-                for (int i = 1; i < g; ++i) { const float x = tokval(grp * g + i, d); mnf = fminf(mnf, x); mxf = fmaxf(mxf, x); }
-                const __half d16 = __float2half_rn(mxf - mnf);
-                const __half sc = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
-                const float scf = __half2float(sc);
-                const int tok0 = s.tk + grp * g;                                        // absolute token of the group's first element
-                uint8_t* blk = ub + (int64_t)(tok0 / kBlockTokens) * bb;
-                *reinterpret_cast<__half*>(blk + lay_scale_off(KB, g, d, (tok0 % kBlockTokens) / g)) = sc;
-                *reinterpret_cast<__half*>(blk + lay_zero_off(KB, g, d, (tok0 % kBlockTokens) / g)) = __float2half_rn(mnf);
+            for (int d = lane; d < kD; d += 32) {
+                uint32_t hw[kSlabs * 16];
+                const bool partial = cnt < kBlockTokens;                                // other fields of the half-words are live data
+                #pragma unroll
+                for (int i = 0; i < kSlabs * 16; ++i)
+                    hw[i] = partial ? *reinterpret_cast<const uint16_t*>(blk + lay_word_off(KB, d, (i >> 4) * kSlabRows + (i & 15)) + 2 * (d & 1)) : 0u;
                 #pragma unroll 1
-                for (int q16 = 0; q16 < g / 16; ++q16) {
-                    const int o0 = (tok0 % kBlockTokens) + 16 * q16;                    // outer index of row 0 of this chunk
-                    const int sl = o0 / kSlabRows, j = (o0 % kSlabRows) / 16;
-                    #pragma unroll 4
-                    for (int row = 0; row < 16; ++row) {
-                        const uint32_t code = (uint32_t)__float2int_rn(q_code(tokval(grp * g + 16 * q16 + row, d), mnf, scf, maxq));
-                        uint16_t* hp = reinterpret_cast<uint16_t*>(blk + lay_word_off(KB, d, sl * kSlabRows + row) + 2 * (d & 1));
-                        *hp = (uint16_t)((*hp & ~(((1u << KB) - 1u) << (KB * j))) | (code << (KB * j)));
+                for (int gl = 0; gl < cnt / g; ++gl) {                                  // groups landing in this block
+                    const int tl0 = bi * kBlockTokens + gl * g;                         // first token of the group within the window
+                    float mnf = INFINITY, mxf = -INFINITY;
+                    #pragma unroll 1
+                    for (int i0 = 0; i0 < g; i0 += 32) {
+                        float x[32];
+                        #pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int t = tl0 + i0 + i;
+                            x[i] = __half2float(t < c.R - 1 ? win[win_off(t, d)] : knew[d]);
+                        }
+                        #pragma unroll
+                        for (int i = 0; i < 32; ++i) { mnf = fminf(mnf, x[i]); mxf = fmaxf(mxf, x[i]); }
+                    }
+                    const __half d16 = __float2half_rn(mxf - mnf);
+                    const __half sc = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
+                    const float scf = __half2float(sc);
+                    const int og = o0 + gl * g;                                         // outer index of the group's first token
+                    *reinterpret_cast<__half*>(blk + lay_scale_off(KB, g, d, og / g)) = sc;
+                    *reinterpret_cast<__half*>(blk + lay_zero_off(KB, g, d, og / g)) = __float2half_rn(mnf);
+                    #pragma unroll 1
+                    for (int q16 = 0; q16 < g / 16; ++q16) {
+                        const int o = og + 16 * q16;                                    // outer index of row 0 of this 16-token chunk
+                        const int sl = o / kSlabRows, j = (o % kSlabRows) / 16;
+                        float x[16];
+                        #pragma unroll
+                        for (int row = 0; row < 16; ++row) {
+                            const int t = tl0 + 16 * q16 + row;
+                            x[row] = __half2float(t < c.R - 1 ? win[win_off(t, d)] : knew[d]);
+                        }
+                        #pragma unroll
+                        for (int row = 0; row < 16; ++row) {
+                            const uint32_t code = (uint32_t)__float2int_rn(q_code(x[row], mnf, scf, maxq));
+                            #pragma unroll
+                            for (int ss = 0; ss < kSlabs; ++ss)                         // compile-time register index, run-time slab
+                                if (ss == sl) hw[ss * 16 + row] = (hw[ss * 16 + row] & ~(((1u << KB) - 1u) << (KB * j))) | (code << (KB * j));
+                        }
                     }
                 }
+                #pragma unroll
+                for (int i = 0; i < kSlabs * 16; ++i)
+                    *reinterpret_cast<uint16_t*>(blk + lay_word_off(KB, d, (i >> 4) * kSlabRows + (i & 15)) + 2 * (d & 1)) = (uint16_t)hw[i];
             }
         }
     }
@@ -525,6 +563,7 @@ qk_kernel(const AttnParams p)
         mbar_fence_init();
     }
     __syncthreads();                                                         // the only CTA barrier: mbarrier init
+    pdl_trigger();                                                           // the p.V kernel may start its prologue
 
     const Sched s = make_sched(c);
     const uint64_t pol = policy_evict_first();
@@ -558,6 +597,7 @@ qk_kernel(const AttnParams p)
             ql[h] = __ldg(reinterpret_cast<const uint2*>(p.q + (int64_t)(row0 + h) * kD) + lane);
         }
     };
+    pdl_wait();                                                              // q / k_new come from the previous kernel of the stream
     fetch_q(unit);
     #pragma unroll 1
     while (left > 0) {
@@ -579,12 +619,9 @@ qk_kernel(const AttnParams p)
         __syncwarp();
         if (left > n_here) fetch_q(unit + 1);                                // the range continues into the next unit
 
-        // lane-local online softmax statistics: (m_blk, s_blk) over the packed-block logits of head h_l held by this lane,
-        // (mw[h], sw[h]) over the window / new-token logits this lane wrote for head h
-        float m_blk = -INFINITY, s_blk = 0.f;
-        float mw[G], sw[G];
-        #pragma unroll
-        for (int h = 0; h < G; ++h) { mw[h] = -INFINITY; sw[h] = 0.f; }
+        // lane-local online softmax statistics: (m_blk, s_blk) over the packed-block logits of head t4 % G held by this lane,
+        // (m_win, s_win) over the window / new-token logits of head lane >> 2 held by this lane
+        float m_blk = -INFINITY, s_blk = 0.f, m_win = -INFINITY, s_win = 0.f;
 
         #pragma unroll 1
         for (int k = 0; k < n_here; ++k, ++j) {
@@ -658,53 +695,45 @@ qk_kernel(const AttnParams p)
                         m_blk = mx; s_blk = a2;
                     }
                 }
-            } else if (j < s.ipu - 1) {                                      // ---- fp16 K window item
-                const int part = lane & 7, tok = lane >> 3;
+            } else if (j < s.ipu - 1) {                                      // ---- fp16 K window item (tensor cores)
+                // D[head][token] = sum_ch q_h[ch] * K[token][ch]: A = q (rows = heads, exact fp16), B = the window rows as they
+                // lie in the stage ([token][channel], swizzled units -> conflict-free fragment loads), 2 tiles of 8 tokens
                 const int t0 = (j - s.n_kb) * kResTile, nt = min(kResTile, s.r - t0);
                 pp.wait();
                 const uint8_t* st = pp.cons();
-                #pragma unroll 1
-                for (int ts = 0; ts < nt; ts += 4) {
-                    const int t = ts + tok;
-                    float sum[G];
-                    #pragma unroll
-                    for (int h = 0; h < G; ++h) sum[h] = 0.f;
-                    if (t < nt) {
-                        const uint4 a4 = *reinterpret_cast<const uint4*>(st + t * 256 + part * 16);
-                        const uint4 b4 = *reinterpret_cast<const uint4*>(st + t * 256 + 128 + part * 16);
-                        const __half2* ah = reinterpret_cast<const __half2*>(&a4);
-                        const __half2* bh = reinterpret_cast<const __half2*>(&b4);
-                        #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
-                            #pragma unroll
-                            for (int h = 0; h < G; ++h) {
-                                const float2 qa = *reinterpret_cast<const float2*>(qlin + h * kD + part * 8 + 2 * e);
-                                const float2 qb = *reinterpret_cast<const float2*>(qlin + h * kD + 64 + part * 8 + 2 * e);
-                                sum[h] = fmaf(qa.x, fa.x, sum[h]); sum[h] = fmaf(qa.y, fa.y, sum[h]);
-                                sum[h] = fmaf(qb.x, fb.x, sum[h]); sum[h] = fmaf(qb.y, fb.y, sum[h]);
-                            }
-                        }
-                    }
-                    #pragma unroll
-                    for (int h = 0; h < G; ++h) {
-                        sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
-                        sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 2);
-                        sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 4);
-                        if (part == 0 && t < nt) {
-                            __half hv = scale_logit(sum[h]);
-                            const int64_t rowi = uq0 + h;
-                            if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + s.tk + t0 + t);
-                            p.w.lg[rowi * p.w.ld + s.tk + t0 + t] = hv;
-                            if (p.dbg_logits) p.dbg_logits[rowi * p.dbg_stride + s.tk + t0 + t] = hv;
-                            const float x1[1] = {__half2float(hv)};
-                            fold_stats(mw[h], sw[h], x1);
-                        }
-                    }
+                float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+                const int g8 = lane >> 2;
+                const int key = (t0 + g8) & 7;                               // swizzle key of rows g8 and g8 + 8 (t0 % 16 == 0)
+                const uint8_t* r0 = st + g8 * 256 + t4 * 4, * r1 = r0 + 8 * 256;
+                #pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    uint2 qa = make_uint2(0u, 0u);
+                    if (g8 < G) qa = q2[(g8 * 8 + cc) * 4 + t4];
+                    const int u0 = ((2 * cc) ^ key) * 16, u1 = ((2 * cc + 1) ^ key) * 16;
+                    mma_16816(d0, qa.x, 0u, qa.y, 0u, *reinterpret_cast<const uint32_t*>(r0 + u0), *reinterpret_cast<const uint32_t*>(r0 + u1));
+                    mma_16816(d1, qa.x, 0u, qa.y, 0u, *reinterpret_cast<const uint32_t*>(r1 + u0), *reinterpret_cast<const uint32_t*>(r1 + u1));
                 }
                 __syncwarp();
                 pp.pop();
                 qk_issue_next<KB>(pp, cur, p, s, lane, pol);
+                // lane (g8 < G, t): head g8, tokens 2t, 2t+1 (tile 0) and 8+2t, 9+2t (tile 1)
+                if (g8 < G) {
+                    const int64_t rowi = uq0 + g8;
+                    float x[4];
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int t = (e >> 1) * 8 + 2 * t4 + (e & 1);
+                        x[e] = -INFINITY;
+                        if (t < nt) {
+                            __half hv = scale_logit(e < 2 ? d0[e] : d1[e - 2]);
+                            if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + s.tk + t0 + t);
+                            p.w.lg[rowi * p.w.ld + s.tk + t0 + t] = hv;
+                            if (p.dbg_logits) p.dbg_logits[rowi * p.dbg_stride + s.tk + t0 + t] = hv;
+                            x[e] = __half2float(hv);
+                        }
+                    }
+                    fold_stats(m_win, s_win, x);
+                }
             } else {                                                         // ---- the new token
                 const uint2 kv = __ldg(reinterpret_cast<const uint2*>(p.k_new + (int64_t)u * kD) + lane);
                 const __half2* kh = reinterpret_cast<const __half2*>(&kv);
@@ -715,14 +744,14 @@ qk_kernel(const AttnParams p)
                     float sum = qv.x * k01.x;
                     sum = fmaf(qv.y, k01.y, sum); sum = fmaf(qv.z, k23.x, sum); sum = fmaf(qv.w, k23.y, sum);
                     sum = warp_sum(sum);
-                    if (lane == 0) {
+                    if (lane == 4 * h) {                                     // the lane that keeps head h's window statistics
                         __half hv = scale_logit(sum);
                         const int64_t rowi = uq0 + h;
                         if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + s.T - 1);
                         p.w.lg[rowi * p.w.ld + s.T - 1] = hv;
                         if (p.dbg_logits) p.dbg_logits[rowi * p.dbg_stride + s.T - 1] = hv;
                         const float x1[1] = {__half2float(hv)};
-                        fold_stats(mw[h], sw[h], x1);
+                        fold_stats(m_win, s_win, x1);
                     }
                 }
             }
@@ -732,7 +761,8 @@ qk_kernel(const AttnParams p)
         const int w_first = rg.owner(unit * s.ipu);
         #pragma unroll
         for (int h = 0; h < G; ++h) {
-            float m = mw[h], sm = sw[h];
+            float m = -INFINITY, sm = 0.f;
+            if ((lane >> 2) == h) { m = m_win; sm = s_win; }
             if (h_l == h && m_blk != -INFINITY) {
                 const float mn = fmaxf(m, m_blk);
                 sm = (m == -INFINITY ? 0.f : sm * fast_exp(m - mn)) + s_blk * fast_exp(m_blk - mn);
@@ -815,7 +845,8 @@ sv_kernel(const AttnParams p)
     const int n_stages = kCW * p.spw;
     uint64_t* full_all = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * p.stage_bytes);
     uint8_t* ptr = smem + (((size_t)n_stages * (p.stage_bytes + 8) + 127) & ~(size_t)127);
-    uint8_t* scratch = ptr + warp * 128;                                     // commit_unit scratch, per warp
+    float* obuf = reinterpret_cast<float*>(ptr) + warp * (G * kD);             // per warp: [G][128] window-item outputs in channel order
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(obuf);                     // commit_unit scratch (128 bytes), same storage
 
     if (tid == 0) {
         for (int i = 0; i < n_stages; ++i) mbar_init(&full_all[i], 1);
@@ -836,6 +867,7 @@ sv_kernel(const AttnParams p)
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
     Cursor cur;
     cur.unit = lo / s.bpu; cur.j = lo - cur.unit * s.bpu; cur.half = 0; cur.left = hi - lo;
+    pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
     for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
@@ -873,15 +905,27 @@ sv_kernel(const AttnParams p)
             #pragma unroll
             for (int e = 0; e < 4; ++e) { qs[h][e] = 0.f; rs[h][e] = 0.f; }
         const float* r0 = p.w.part + (int64_t)un * p.w.part_cap * rec;
+        constexpr int kBatch = G == 1 ? 4 : 2;                               // records loaded per round trip (independent loads)
         #pragma unroll 1
-        for (int w = 0; w < nparts; ++w) {
+        for (int w0 = 0; w0 < nparts; w0 += kBatch) {
+            float4 a[kBatch][G], b4[kBatch][G];
             #pragma unroll
-            for (int h = 0; h < G; ++h) {
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 0) * kD) + lane);
-                const float4 b4 = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)w * rec + (h * 2 + 1) * kD) + lane);
-                qs[h][0] += a.x; qs[h][1] += a.y; qs[h][2] += a.z; qs[h][3] += a.w;
-                rs[h][0] += b4.x; rs[h][1] += b4.y; rs[h][2] += b4.z; rs[h][3] += b4.w;
-            }
+            for (int k = 0; k < kBatch; ++k)
+                #pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    a[k][h] = make_float4(0.f, 0.f, 0.f, 0.f); b4[k][h] = a[k][h];
+                    if (w0 + k < nparts) {
+                        a[k][h] = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)(w0 + k) * rec + (h * 2 + 0) * kD) + lane);
+                        b4[k][h] = __ldcg(reinterpret_cast<const float4*>(r0 + (int64_t)(w0 + k) * rec + (h * 2 + 1) * kD) + lane);
+                    }
+                }
+            #pragma unroll
+            for (int k = 0; k < kBatch; ++k)                                 // fixed order: the sum does not depend on who arrives last
+                #pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    qs[h][0] += a[k][h].x; qs[h][1] += a[k][h].y; qs[h][2] += a[k][h].z; qs[h][3] += a[k][h].w;
+                    rs[h][0] += b4[k][h].x; rs[h][1] += b4[k][h].y; rs[h][2] += b4[k][h].z; rs[h][3] += b4[k][h].w;
+                }
         }
         #pragma unroll
         for (int h = 0; h < G; ++h) {
@@ -976,11 +1020,13 @@ sv_kernel(const AttnParams p)
                 float zsel[NG];
                 gather_z<G, GS>(zc, lane, zsel);
                 finalize<VB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int, float v) { run[slot] += v; });
-            } else if (j < s.bpu - 1) {                                      // ---- fp16 V window item
+            } else if (j < s.bpu - 1) {                                      // ---- fp16 V window item (tensor cores)
+                // D[channel][head] = sum_tok V[tok][channel] * p_h[tok]: A = the window rows as they lie in the stage
+                // ([token][channel], swizzled units), delivered transposed by ldmatrix; B = the probabilities (exact fp16)
                 const int i = j - s.n_vb;
-                int l0, nt;                                                  // logical index of the item's first token
-                if (i < s.vr1) { l0 = i * kResTile; nt = min(kResTile, s.seg1 - l0); }
-                else { const int tt0 = (i - s.vr1) * kResTile; l0 = s.seg1 + tt0; nt = min(kResTile, s.L - s.seg1 - tt0); }
+                int l0, nt, slot0;                                           // logical index / ring slot of the item's first token
+                if (i < s.vr1) { l0 = i * kResTile; nt = min(kResTile, s.seg1 - l0); slot0 = s.vhead + l0; }
+                else { const int tt0 = (i - s.vr1) * kResTile; l0 = s.seg1 + tt0; nt = min(kResTile, s.L - s.seg1 - tt0); slot0 = tt0; }
                 // the item's probabilities: lane t < nt computes token tv + l0 + t
                 float pl[G];
                 #pragma unroll
@@ -993,23 +1039,53 @@ sv_kernel(const AttnParams p)
                         pl[h] = __half2float(pr);
                     }
                 }
+                const int g8 = lane >> 2;
+                uint32_t b0 = 0u, b1 = 0u;                                   // column g8 = head g8: tokens 2t, 2t+1 | 2t+8, 2t+9
+                #pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    const float p0 = __shfl_sync(0xffffffffu, pl[h], 2 * t4), p1 = __shfl_sync(0xffffffffu, pl[h], 2 * t4 + 1);
+                    const float p2 = __shfl_sync(0xffffffffu, pl[h], 2 * t4 + 8), p3 = __shfl_sync(0xffffffffu, pl[h], 2 * t4 + 9);
+                    if (g8 == h) { b0 = h2_as_u32(__floats2half2_rn(p0, p1)); b1 = h2_as_u32(__floats2half2_rn(p2, p3)); }
+                }
                 pp.wait();
-                const uint8_t* st = pp.cons();
-                #pragma unroll 2
-                for (int t = 0; t < nt; ++t) {
-                    const uint2 vv = *reinterpret_cast<const uint2*>(st + t * 256 + lane * 8);
-                    const __half2* vh = reinterpret_cast<const __half2*>(&vv);
-                    const float2 v01 = __half22float2(vh[0]), v23 = __half22float2(vh[1]);
+                uint8_t* st = pp.cons();
+                if (nt < kResTile) {                                         // rows past the item hold stale bytes (maybe NaN patterns)
+                    for (int idx = lane; idx < (kResTile - nt) * 16; idx += 32)
+                        *reinterpret_cast<uint4*>(st + nt * 256 + idx * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    __syncwarp();
+                }
+                // ldmatrix: lanes 8i .. 8i+7 address the rows of matrix i = (tokens 8*(i>>1) .., channel unit 2*mt + (i&1))
+                const int tr = ((lane >> 4) << 3) + (lane & 7);
+                const uint8_t* rowp = st + tr * 256;
+                const int key = (slot0 + tr) & 7, usel = (lane >> 3) & 1;
+                float oacc[8][4];
+                #pragma unroll
+                for (int mt = 0; mt < 8; ++mt) {
                     #pragma unroll
-                    for (int h = 0; h < G; ++h) {
-                        const float pr = __shfl_sync(0xffffffffu, pl[h], t);
-                        orr[h][0] = fmaf(pr, v01.x, orr[h][0]); orr[h][1] = fmaf(pr, v01.y, orr[h][1]);
-                        orr[h][2] = fmaf(pr, v23.x, orr[h][2]); orr[h][3] = fmaf(pr, v23.y, orr[h][3]);
-                    }
+                    for (int e = 0; e < 4; ++e) oacc[mt][e] = 0.f;
+                    uint32_t af[4];
+                    ldmatrix_x4_trans(af, rowp + (((2 * mt + usel) ^ key) << 4));
+                    mma_16816(oacc[mt], af[0], af[1], af[2], af[3], b0, b1);
                 }
                 __syncwarp();
                 pp.pop();
                 sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
+                // lane (g8, t): oacc[mt] = D[16mt + g8 | + 8][heads 2t, 2t+1] -> channel order through shared memory
+                #pragma unroll
+                for (int mt = 0; mt < 8; ++mt)
+                    #pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (2 * t4 + e < G) {
+                            obuf[(2 * t4 + e) * kD + 16 * mt + g8] = oacc[mt][e];
+                            obuf[(2 * t4 + e) * kD + 16 * mt + g8 + 8] = oacc[mt][2 + e];
+                        }
+                __syncwarp();
+                #pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    const float4 v = *reinterpret_cast<const float4*>(obuf + h * kD + lane * 4);
+                    orr[h][0] += v.x; orr[h][1] += v.y; orr[h][2] += v.z; orr[h][3] += v.w;
+                }
+                __syncwarp();
             } else {                                                         // ---- the new token (v_new)
                 const uint2 vv = __ldg(reinterpret_cast<const uint2*>(p.v_new + (int64_t)u * kD) + lane);
                 const __half2* vh = reinterpret_cast<const __half2*>(&vv);
@@ -1108,7 +1184,7 @@ static int launch_attention(AttnParams& p, cudaStream_t st)
     const int half_v = kHalfChunks * Lay<VB>::kChunkBytes + lay_meta_bytes(c.g) / kParts + G * kPartTokens * 2;
     const int stage = max(max(half_k, half_v), kResBytes);
     p.stage_bytes = (stage + 127) / 128 * 128;
-    const int fixed = 512 + max(kCW * G * (32 * 8 + kD * 4), kCW * 128);     // barriers + per-warp q buffers / commit scratch
+    const int fixed = 512 + kCW * G * (32 * 8 + kD * 4);                     // barriers + per-warp q buffers (qk) / window outputs (sv)
     int ctas = G == 1 ? kMaxCtasPerSm : 2;                                   // the kernels' __launch_bounds__
     p.spw = 0;
     for (; ctas >= 1; --ctas) {                                              // most CTAs per SM that still get >= 2 stages per warp
@@ -1137,9 +1213,19 @@ static int launch_attention(AttnParams& p, cudaStream_t st)
     // ranges per unit than the workspace has record / statistics slots: part_cap - 2 warps per unit at most
     const long long want = (long long)p.n_units * max(1, p.w.part_cap - 2);
     p.nw_eff = (int)min((long long)grid * kCW, want);
-    kqk<<<grid, kThreads, smem, st>>>(p);
+    // both launches carry the programmatic-serialization attribute: the q.K^T prologue (setup, state, first K blocks in
+    // flight) overlaps the tail of the previous kernel of the stream, the p.V prologue overlaps the q.K^T tail
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = getenv("KIVI_NO_PDL") ? 0 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kqk, p);
+    if (e != cudaSuccess) return (int)e;
     int rc = post_launch(); if (rc) return rc;
-    ksv<<<grid, kThreads, smem, st>>>(p);
+    e = cudaLaunchKernelEx(&cfg, ksv, p);
+    if (e != cudaSuccess) return (int)e;
     return post_launch();
 }
 

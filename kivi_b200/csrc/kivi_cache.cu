@@ -94,11 +94,11 @@ residual_prefill_kernel(CacheDesc c, const __half* __restrict__ k, const __half*
 {
     const int u = blockIdx.x;
     const int r = n - nqk, L = n - nqv;
-    for (int i = threadIdx.x; i < r * (kD / 8); i += blockDim.x)
-        reinterpret_cast<uint4*>(c.k_res + (int64_t)u * c.R * kD)[i] =
+    for (int i = threadIdx.x; i < r * (kD / 8); i += blockDim.x)                 // window rows are unit-swizzled (win_unit)
+        reinterpret_cast<uint4*>(c.k_res + (int64_t)u * c.R * kD)[win_unit(i / 16, i % 16)] =
             __ldg(reinterpret_cast<const uint4*>(k + ((int64_t)u * n + nqk) * kD) + i);
     for (int i = threadIdx.x; i < L * (kD / 8); i += blockDim.x)
-        reinterpret_cast<uint4*>(c.v_res + (int64_t)u * c.v_res_cap * kD)[i] =
+        reinterpret_cast<uint4*>(c.v_res + (int64_t)u * c.v_res_cap * kD)[win_unit(i / 16, i % 16)] =
             __ldg(reinterpret_cast<const uint4*>(v + ((int64_t)u * n + nqv) * kD) + i);
     if (u == 0 && threadIdx.x == 0) {
         c.state[ST_TK] = nqk; c.state[ST_R] = r; c.state[ST_TV] = nqv; c.state[ST_L] = L;
@@ -176,10 +176,10 @@ export_kv_kernel(CacheDesc c, int tk, int tv, int L, int vhead, int r,
         }
     }
     for (int i = tid; i < r * kD; i += stride)
-        k_full[(int64_t)u * r * kD + i] = c.k_res[(int64_t)u * c.R * kD + i];
+        k_full[(int64_t)u * r * kD + i] = c.k_res[(int64_t)u * c.R * kD + win_off(i / kD, i % kD)];
     for (int i = tid; i < L * kD; i += stride) {
         const int t = i / kD, d = i % kD;
-        v_full[(int64_t)u * L * kD + i] = c.v_res[((int64_t)u * c.v_res_cap + (vhead + t) % c.v_res_cap) * kD + d];
+        v_full[(int64_t)u * L * kD + i] = c.v_res[(int64_t)u * c.v_res_cap * kD + win_off((vhead + t) % c.v_res_cap, d)];
     }
 }
 

@@ -21,7 +21,9 @@
 //   its half2 of x (q or p) to build its B fragment, and its four registers ARE the A operand of the zero-term
 //   MMA (rows 0..7 = zeros of group G; rows 8..15 = the scales, whose products are ignored).
 //
-//   K window [U][R][128] fp16            V window [U][R+1][128] fp16 ring buffer (head = state.vhead)
+//   K window [U][R][128] fp16, V window [U][R+1][128] fp16 ring (head = state.vhead).  Inside a 256-byte row the eight-
+//   channel (16-byte) units are XOR-swizzled with the row's slot index: unit' = unit ^ (slot & 7)  (win_off below), so that
+//   the MMA fragment loads of 8 consecutive rows at one channel offset hit 8 different bank groups of shared memory.
 //   state    int32[8] on the device, shared by the layers of a model: {tk, r, tv, L, vhead, kv_len}
 //
 // Policy restated from models/llama_kivi.py:343-356 (K: the fp16 window is quantised per channel in
@@ -84,6 +86,11 @@ __host__ __device__ inline int lay_bit_pos(int bits, int i, int o) {
     const int F = 16 / bits, slab_rows = 16 * F;
     return 16 * (i & 1) + bits * ((o % slab_rows) >> 4);
 }
+// element offset (halfs, inside a unit's window) of (slot, channel): 16-byte units swizzled with the slot index
+__host__ __device__ inline int win_off(int slot, int ch) { return slot * kD + ((((ch >> 3) ^ (slot & 7)) << 3) | (ch & 7)); }
+// the same for a 16-byte unit index (0..15) of the row
+__host__ __device__ inline int win_unit(int slot, int unit) { return slot * 16 + (unit ^ (slot & 7)); }
+
 // byte offsets (inside a block) of the fp16 zero / scale of (inner i, outer group G)
 __host__ __device__ inline int lay_zero_off(int bits, int g, int i, int G) {
     const int c = i >> 4, ii = i & 15;
@@ -144,6 +151,13 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// four 8x8 b16 matrices from shared memory, each delivered TRANSPOSED: lane (g8, t) receives, of matrix i, the elements
+// (memory row 2t, column g8) and (memory row 2t+1, column g8); lanes 8i .. 8i+7 supply the row addresses of matrix i
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(row_ptr)));
 }
 
 }  // namespace kivi

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--bits", type=int, default=2)
     ap.add_argument("--g", type=int, default=32)
     ap.add_argument("--R", type=int, default=128)
+    ap.add_argument("--only-fused", action="store_true", help="time only the decode attention on the blocked cache")
     a = ap.parse_args()
     from kivi_b200 import matmul, new_pack
     dev = "cuda"
@@ -63,6 +64,21 @@ def main():
     res["copy_GBps"] = 2 * src.numel() / best / 1e6
     del src, dst
 
+    if not a.only_fused:
+        generic_part(a, res, gen, flush, dev)
+    fused_part(a, res, gen, flush, dev)
+    if a.out:
+        os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+        with open(a.out, "w") as f:
+            json.dump(res, f, indent=1)
+    print(json.dumps(res))
+
+
+def generic_part(a, res, gen, flush, dev):
+    from kivi_b200 import matmul, new_pack
+    B, H, Hkv, D, T, bits, g, R = a.B, a.H, a.Hkv, 128, a.T, a.bits, a.g, a.R
+    Tk = (T - 1) // R * R
+    Tv = T - 1 - R
     kT = torch.randn((B, Hkv, D, Tk), generator=gen, device=dev, dtype=torch.float16)
     kc, ks, kz = new_pack.triton_quantize_and_pack_along_last_dim(kT, g, bits)
     del kT
@@ -91,9 +107,14 @@ def main():
     res["ours_pack_k_flush_ms"] = ms
     res["ours_pack_k_flush_GBps"] = (kres.numel() * 2 * (1 + (bits / 8 + 4 / g) / 2)) / ms / 1e6
 
-    # fused decode attention on the blocked cache (one launch: qK + softmax + pV + cache update)
+    if a.ref:
+        reference_part(a, res, gen, flush, dev, q, pq, bytes_qk, bytes_sv)
+
+
+def fused_part(a, res, gen, flush, dev):
+    """decode attention on the blocked cache (two launches: q.K^T + statistics, p.V + output + cache update)"""
     from kivi_b200.cache import KiviCache
-    del kc, ks, kz, vc, vs, vz
+    B, H, Hkv, D, T, bits, g, R = a.B, a.H, a.Hkv, 128, a.T, a.bits, a.g, a.R
     cache = KiviCache(1, B, H, Hkv, 128, bits, bits, g, R, max_tokens=T + 256)
     nfill = T - 1 - R // 2                                            # mid-window state (no K flush in the timed call)
     kk = torch.randn((B, Hkv, nfill, D), generator=gen, device=dev, dtype=torch.float16)
@@ -114,7 +135,14 @@ def main():
     res["fused_bytes"] = bytes_fused
     ms2, _ = timeit(lambda: cache.decode_attention(0, qd, kn, vn, out=outd), iters=30)   # no L2 flush (cache >> L2 anyway)
     res["fused_decode_noflush_ms"] = ms2
-    if a.ref:
+
+
+def reference_part(a, res, gen, flush, dev, q, pq, bytes_qk, bytes_sv):
+    from kivi_b200 import matmul, new_pack
+    B, H, Hkv, D, T, bits, g, R = a.B, a.H, a.Hkv, 128, a.T, a.bits, a.g, a.R
+    Tk = (T - 1) // R * R
+    Tv = T - 1 - R
+    if True:
         kT = torch.randn((B, Hkv, D, Tk), generator=gen, device=dev, dtype=torch.float16)
         kc, ks, kz = new_pack.triton_quantize_and_pack_along_last_dim(kT, g, bits)
         del kT
@@ -153,11 +181,6 @@ def main():
             ms, _ = timeit(lambda: refmod.gemv_forward_cuda_outer_dim(p2, vc2, vs2, vz2, bits, g, H, Hkv), flush=flush, iters=10)
             res["ref_sv_kernel_ms"] = ms
             res["ref_sv_kernel_GBps"] = bytes_sv / ms / 1e6
-    print(json.dumps(res))
-    if a.out:
-        os.makedirs(os.path.dirname(a.out), exist_ok=True)
-        with open(a.out, "w") as f:
-            json.dump(res, f, indent=1)
 
 
 if __name__ == "__main__":
