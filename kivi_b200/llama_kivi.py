@@ -436,9 +436,12 @@ class LlamaForCausalLM_KIVI(nn.Module):
                 for bufs, (kr, vr) in zip(self.cache._bufs, snap):
                     bufs[2].copy_(kr)
                     bufs[3].copy_(vr)
+                from . import _lib
+                n0 = _lib.launch_count()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._step_body()
+                self.launches_per_step = _lib.launch_count() - n0            # libkivi_b200 launches replayed by every step
                 # capture does not execute: state is still the pre-step state
                 self._graph = g
             self._graph.replay()
