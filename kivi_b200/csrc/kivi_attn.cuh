@@ -506,7 +506,7 @@ __device__ __forceinline__ void fold_stats(float& m, float& s, const float (&x)[
 // ------------------------------------------------------------------------------------------------
 // q . K^T  (+ scale, mask, per-range softmax statistics)
 // ------------------------------------------------------------------------------------------------
-template <int KB>
+template <int KB, int GS>
 __device__ __forceinline__ void qk_issue_next(Pipe& pp, Cursor& cur, const AttnParams& p, const Sched& s,
                                               int lane, uint64_t pol)
 {
@@ -522,8 +522,8 @@ __device__ __forceinline__ void qk_issue_next(Pipe& pp, Cursor& cur, const AttnP
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (cur.j < s.n_kb) {
             constexpr int cb = kHalfChunks * Lay<KB>::kChunkBytes;    // codes of a stage-item
-            const int mb = lay_meta_bytes(c.g) / kParts;
-            const uint8_t* blk = c.k_store + ((int64_t)u * c.k_cap_blocks + cur.j) * lay_block_bytes(KB, c.g);
+            const int mb = lay_meta_bytes(GS) / kParts;
+            const uint8_t* blk = c.k_store + ((int64_t)u * c.k_cap_blocks + cur.j) * lay_block_bytes(KB, GS);
             mbar_expect_tx(bar, (uint32_t)(cb + mb));
             if (kParts == 1) {
                 bulk_g2s(dst, blk, (uint32_t)(cb + mb), bar, pol);    // codes and meta are contiguous: one copy
@@ -577,7 +577,7 @@ qk_kernel(const AttnParams p)
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
     Cursor cur;
     cur.unit = lo / s.ipu; cur.j = lo - cur.unit * s.ipu; cur.half = 0; cur.left = hi - lo;
-    for (int i = 0; i < p.spw; ++i) qk_issue_next<KB>(pp, cur, p, s, lane, pol);
+    for (int i = 0; i < p.spw; ++i) qk_issue_next<KB, GS>(pp, cur, p, s, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
     const int ratio = c.H / c.Hkv;
@@ -641,7 +641,7 @@ qk_kernel(const AttnParams p)
                     }, acc, zc, lane);
                     __syncwarp();
                     pp.pop();
-                    qk_issue_next<KB>(pp, cur, p, s, lane, pol);
+                    qk_issue_next<KB, GS>(pp, cur, p, s, lane, pol);
                 }
                 float zsel[NG];
                 gather_z<G, GS>(zc, lane, zsel);
@@ -649,28 +649,16 @@ qk_kernel(const AttnParams p)
                 __half* row = p.w.lg + rowi * p.w.ld + j * kBlockTokens;
                 const int nvalid = s.tk - j * kBlockTokens;                  // < 128 only in the last block when R < 128
                 if (!slow && nvalid >= kBlockTokens) {
-                    if (G == 1 && GS == 32) {                                // exactly four logits per lane
-                        float x[4];
+                    {                                                        // the lane's logits by compile-time slot
+                        float x[Slots<G, GS>::k];
+                        #pragma unroll
+                        for (int e = 0; e < Slots<G, GS>::k; ++e) x[e] = -INFINITY;  // slots of MMAs this lane does not own
                         finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int o, float v) {
                             const __half hv = scale_logit(v);
                             row[o] = hv;
                             x[slot] = __half2float(hv);
                         });
                         fold_stats(m_blk, s_blk, x);
-                    } else {
-                        float mx = m_blk;
-                        finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
-                            const __half hv = scale_logit(v);
-                            row[o] = hv;
-                            mx = fmaxf(mx, __half2float(hv));
-                        });
-                        if (mx != -INFINITY) {
-                            float a2 = s_blk * fast_exp(m_blk - mx);
-                            finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
-                                a2 += fast_exp(__half2float(scale_logit(v)) - mx);
-                            });
-                            m_blk = mx; s_blk = a2;
-                        }
                     }
                 } else {
                     auto logit_of = [&](int o, float v) -> __half {          // fp16 scaled (+ mask): the softmax input
@@ -715,7 +703,7 @@ qk_kernel(const AttnParams p)
                 }
                 __syncwarp();
                 pp.pop();
-                qk_issue_next<KB>(pp, cur, p, s, lane, pol);
+                qk_issue_next<KB, GS>(pp, cur, p, s, lane, pol);
                 // lane (g8 < G, t): head g8, tokens 2t, 2t+1 (tile 0) and 8+2t, 9+2t (tile 1)
                 if (g8 < G) {
                     const int64_t rowi = uq0 + g8;
@@ -781,7 +769,7 @@ qk_kernel(const AttnParams p)
 // ------------------------------------------------------------------------------------------------
 // p . V  (+ softmax normalisation, output, cache update)
 // ------------------------------------------------------------------------------------------------
-template <int VB, int G>
+template <int VB, int G, int GS>
 __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnParams& p, const Sched& s,
                                               int ratio, int lane, uint64_t pol)
 {
@@ -797,8 +785,8 @@ __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnP
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (cur.j < s.n_vb) {
             constexpr int cb = kHalfChunks * Lay<VB>::kChunkBytes;    // codes of a stage-item
-            const int mb = lay_meta_bytes(c.g) / kParts;
-            const uint8_t* blk = c.v_store + ((int64_t)u * c.v_cap_blocks + cur.j) * lay_block_bytes(VB, c.g);
+            const int mb = lay_meta_bytes(GS) / kParts;
+            const uint8_t* blk = c.v_store + ((int64_t)u * c.v_cap_blocks + cur.j) * lay_block_bytes(VB, GS);
             mbar_expect_tx(bar, (uint32_t)(cb + mb + G * kPartTokens * 2));
             if (kParts == 1) {
                 bulk_g2s(dst, blk, (uint32_t)(cb + mb), bar, pol);    // codes and meta are contiguous: one copy
@@ -868,7 +856,7 @@ sv_kernel(const AttnParams p)
     Cursor cur;
     cur.unit = lo / s.bpu; cur.j = lo - cur.unit * s.bpu; cur.half = 0; cur.left = hi - lo;
     pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
-    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
+    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
     const int h_l = t4 % G;
@@ -1015,7 +1003,7 @@ sv_kernel(const AttnParams p)
                     }, acc, zc, lane);
                     __syncwarp();
                     pp.pop();
-                    sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
+                    sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
                 }
                 float zsel[NG];
                 gather_z<G, GS>(zc, lane, zsel);
@@ -1069,7 +1057,7 @@ sv_kernel(const AttnParams p)
                 }
                 __syncwarp();
                 pp.pop();
-                sv_issue_next<VB, G>(pp, cur, p, s, ratio, lane, pol);
+                sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
                 // lane (g8, t): oacc[mt] = D[16mt + g8 | + 8][heads 2t, 2t+1] -> channel order through shared memory
                 #pragma unroll
                 for (int mt = 0; mt < 8; ++mt)
