@@ -172,6 +172,7 @@ def workload_config(args):
 # main arm
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
+    os.environ.setdefault("NCCL_DEBUG", "WARN")              # keep NCCL's version banner off stdout: one JSON line only
     import torch
     from kivi_b200 import _lib, dist as kdist
     from kivi_b200.llama_kivi import LlamaForCausalLM_KIVI, default_config
@@ -298,7 +299,7 @@ def run_ours(args):
             pass
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_decode_attention_ncu.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01_attention_ncu.json")) as f:      # ncu --set full, both kernels of the call
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -331,6 +332,8 @@ def run_ours(args):
                                      f"captured and replayed from a CUDA graph: per layer q.K^T + p.V attention kernels, "
                                      f"add+RMSNorm x2, RoPE+split, SiLU*mul; final norm; cache advance (cuBLAS GEMMs not counted)",
                 "roofline": roof, "cpu_baseline": cpu, "cache_state_after_timed": state_at_end,
+                "note": "the timed steps end at seq 4096 and therefore include the once-per-128-steps K flush step (tk 3968 -> 4096); "
+                        "the e2e steps follow at seq 4097..",
                 "model": args.model, "global_batch": Bg}
         print(json.dumps(line))
     if ws > 1:

@@ -40,7 +40,7 @@
 
 // tuning knobs of the chunk loop (tools/build_variants.py measures the alternatives)
 #ifndef KIVI_UNROLL
-#define KIVI_UNROLL 4
+#define KIVI_UNROLL 8
 #endif
 constexpr int kChunkUnroll = KIVI_UNROLL;
 #ifndef KIVI_SHIFT_IMAD
@@ -171,7 +171,7 @@ struct Cols {
 //             columns 2t, 2t+1 = (group-in-fragment t / G, head t % G, hi | lo)
 //   zc      : zero-term accumulator: row g8 = group min(g8 >> 1, NG-1), columns 2t, 2t+1 = head t % G
 // ------------------------------------------------------------------------------------------------
-template <int BITS, int G, int GS, class XF>
+template <int BITS, int G, int GS, bool INIT, class XF>
 __device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, float (&acc)[8][4], float (&zc)[4], int lane)
 {
     using L = Lay<BITS>;
@@ -190,7 +190,8 @@ __device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, f
         getx(c0 + cl, hb, xa, xb);
         // {z(2t,2t+1), s(2t,2t+1), z(2t+8,2t+9), s(2t+8,2t+9)} of group gz: as is, the A operand of the zero-term MMA
         const uint4 mz = *reinterpret_cast<const uint4*>(meta + (cl * NG + gz) * 64);
-        mma_16816(zc, mz.x, mz.y, mz.z, mz.w, xa, xb);
+        if (INIT && cl == 0) mma_16816_init(zc, mz.x, mz.y, mz.z, mz.w, xa, xb);      // first chunk of a block: D = A * B
+        else mma_16816(zc, mz.x, mz.y, mz.z, mz.w, xa, xb);
         uint32_t b0[NF], b1[NF];
         if (G == 1 && NF == 1) {                        // the B column's group is gz
             b0[0] = b_prep(xa, mz.y, msel); b1[0] = b_prep(xb, mz.w, msel);
@@ -226,7 +227,8 @@ __device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, f
                 }
                 const int mm = sl * L::F + j;
                 const int f = ((16 * mm) / GS) / GPF;
-                mma_16816(acc[mm], a[0], a[1], a[2], a[3], b0[f], b1[f]);
+                if (INIT && cl == 0) mma_16816_init(acc[mm], a[0], a[1], a[2], a[3], b0[f], b1[f]);
+                else mma_16816(acc[mm], a[0], a[1], a[2], a[3], b0[f], b1[f]);
             }
         }
     }
@@ -627,15 +629,19 @@ qk_kernel(const AttnParams p)
         for (int k = 0; k < n_here; ++k, ++j) {
             if (j < s.n_kb) {                                                // ---- packed K block (tensor cores)
                 float acc[8][4];
-                float zc[4] = {0.f, 0.f, 0.f, 0.f};
-                #pragma unroll
-                for (int mm = 0; mm < 8; ++mm)
+                float zc[4];
+                if (kParts > 1) {                                            // whole-block stages start from D = A * B instead
                     #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
+                    for (int mm = 0; mm < 8; ++mm)
+                        #pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) zc[e] = 0.f;
+                }
                 #pragma unroll 1
                 for (int half = 0; half < kParts; ++half) {
                     pp.wait();
-                    mma_half<KB, G, GS>(pp.cons(), half * kHalfChunks, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
+                    mma_half<KB, G, GS, kParts == 1>(pp.cons(), half * kHalfChunks, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
                         const uint2 v = q2[(h * 8 + cc) * 4 + t4];
                         xa = v.x; xb = v.y;
                     }, acc, zc, lane);
@@ -968,11 +974,15 @@ sv_kernel(const AttnParams p)
         for (int k = 0; k < n_here; ++k, ++j) {
             if (j < s.n_vb) {                                                // ---- packed V block (tensor cores)
                 float acc[8][4];
-                float zc[4] = {0.f, 0.f, 0.f, 0.f};
-                #pragma unroll
-                for (int mm = 0; mm < 8; ++mm)
+                float zc[4];
+                if (kParts > 1) {
                     #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
+                    for (int mm = 0; mm < 8; ++mm)
+                        #pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[mm][e] = 0.f;
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) zc[e] = 0.f;
+                }
                 #pragma unroll 1
                 for (int half = 0; half < kParts; ++half) {
                     const int t0 = j * kBlockTokens + half * kPartTokens, nt = s.tv - t0;   // nt >= kPartTokens except at the end of the store
@@ -996,7 +1006,7 @@ sv_kernel(const AttnParams p)
                         }
                     }
                     __syncwarp();
-                    mma_half<VB, G, GS>(st, half * kHalfChunks, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
+                    mma_half<VB, G, GS, kParts == 1>(st, half * kHalfChunks, [&](int cc, int h, uint32_t& xa, uint32_t& xb) {
                         const __half* pr = prob + h * kPartTokens + 16 * (cc - half * kHalfChunks) + 2 * t4;
                         xa = *reinterpret_cast<const uint32_t*>(pr);
                         xb = *reinterpret_cast<const uint32_t*>(pr + 8);

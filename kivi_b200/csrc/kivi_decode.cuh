@@ -153,6 +153,14 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// D = A * B (no accumulator input: the zero registers are free, and no instruction is spent clearing D beforehand)
+__device__ __forceinline__ void mma_16816_init(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+
 // four 8x8 b16 matrices from shared memory, each delivered TRANSPOSED: lane (g8, t) receives, of matrix i, the elements
 // (memory row 2t, column g8) and (memory row 2t+1, column g8); lanes 8i .. 8i+7 supply the row addresses of matrix i
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* row_ptr) {
