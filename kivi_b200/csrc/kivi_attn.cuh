@@ -43,6 +43,12 @@
 #define KIVI_UNROLL 8
 #endif
 constexpr int kChunkUnroll = KIVI_UNROLL;
+#ifndef KIVI_Z_SIMT
+#define KIVI_Z_SIMT 0                    // 1: zero term of G == 1 kernels with FFMAs instead of one MMA per chunk (measured: see DESIGN.md)
+#endif
+#ifndef KIVI_EVICT_FIRST
+#define KIVI_EVICT_FIRST 1
+#endif
 #ifndef KIVI_SHIFT_IMAD
 #define KIVI_SHIFT_IMAD 0
 #endif
@@ -190,7 +196,13 @@ __device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, f
         getx(c0 + cl, hb, xa, xb);
         // {z(2t,2t+1), s(2t,2t+1), z(2t+8,2t+9), s(2t+8,2t+9)} of group gz: as is, the A operand of the zero-term MMA
         const uint4 mz = *reinterpret_cast<const uint4*>(meta + (cl * NG + gz) * 64);
-        if (INIT && cl == 0) mma_16816_init(zc, mz.x, mz.y, mz.z, mz.w, xa, xb);      // first chunk of a block: D = A * B
+        if (KIVI_Z_SIMT && G == 1) {
+            // zero term on the FMA pipe: this lane's four inner indices of (group gz); zc[0] collects the lane's partial sum
+            const float2 x0 = __half22float2(u32_as_h2(xa)), x1 = __half22float2(u32_as_h2(xb));
+            const float2 z0 = __half22float2(u32_as_h2(mz.x)), z1 = __half22float2(u32_as_h2(mz.z));
+            float zp = (INIT && cl == 0) ? x0.x * z0.x : fmaf(x0.x, z0.x, zc[0]);
+            zp = fmaf(x0.y, z0.y, zp); zp = fmaf(x1.x, z1.x, zp); zc[0] = fmaf(x1.y, z1.y, zp);
+        } else if (INIT && cl == 0) mma_16816_init(zc, mz.x, mz.y, mz.z, mz.w, xa, xb);   // first chunk of a block: D = A * B
         else mma_16816(zc, mz.x, mz.y, mz.z, mz.w, xa, xb);
         uint32_t b0[NF], b1[NF];
         if (G == 1 && NF == 1) {                        // the B column's group is gz
@@ -237,9 +249,14 @@ __device__ __forceinline__ void mma_half(const uint8_t* st, int c0, XF&& getx, f
 // The lane's zero term for every outer group: Z[head t % G][grp] lives in the lanes with g8 = 2 * grp.
 template <int G, int GS>
 __device__ __forceinline__ void gather_z(const float (&zc)[4], int lane, float (&zsel)[Cols<G, GS>::NG]) {
+    float z = zc[0];
+    if (KIVI_Z_SIMT && G == 1) {                        // the four t-lanes of a g8 row hold partial sums of its group
+        z += __shfl_xor_sync(0xffffffffu, z, 1);
+        z += __shfl_xor_sync(0xffffffffu, z, 2);
+    }
     #pragma unroll
     for (int grp = 0; grp < Cols<G, GS>::NG; ++grp)
-        zsel[grp] = __shfl_sync(0xffffffffu, zc[0], 8 * grp + (lane & 3));
+        zsel[grp] = __shfl_sync(0xffffffffu, z, 8 * grp + (lane & 3));
 }
 
 // branch-free v[t] for t = (t2, t1): three SELP (the compiler turns long ?: chains over registers into branches)
@@ -568,7 +585,7 @@ qk_kernel(const AttnParams p)
     pdl_trigger();                                                           // the p.V kernel may start its prologue
 
     const Sched s = make_sched(c);
-    const uint64_t pol = policy_evict_first();
+    const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
     const long long N = (long long)p.n_units * s.ipu;                        // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);
@@ -849,7 +866,7 @@ sv_kernel(const AttnParams p)
     __syncthreads();                                                         // the only CTA barrier: mbarrier init
 
     const Sched s = make_sched(c);
-    const uint64_t pol = policy_evict_first();
+    const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
     const long long N = (long long)p.n_units * s.bpu;                       // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);                        // range owners: every range is non-empty
