@@ -283,3 +283,46 @@ def test_full_size_consistency(mode):
     _stage_checks(st, to_np(q[sl, :2])[:, :, None, :], to_np(kn[sl, :2])[:, :, None, :], to_np(vn[sl, :2])[:, :, None, :],
                   g, 2, 2, R, to_np(out[sl, :2])[:, :, None, :], to_np(dbg_s[sl, :2])[:, :, None, :],
                   to_np(dbg_p[sl, :2])[:, :, None, :])
+
+
+@pytest.mark.parametrize("B,H,Hkv,kb,vb,g,R,n0", [(1, 8, 2, 4, 4, 64, 64, 20000),      # cfg-4-like: few, long units, GQA 4, 4-bit
+                                                  (2, 4, 4, 2, 2, 32, 128, 9000)])     # MHA, more ranges per unit than warps of a CTA
+def test_long_context_many_ranges_per_unit(B, H, Hkv, kb, vb, g, R, n0):
+    """Few long units: every unit is cut into many warp ranges (more than 32 statistic slots and partial records per
+    unit), far beyond what a logits row in shared memory could hold.  Checked against the library's generic-layout
+    kernels run on the exported cache (an independent code path) and against the softmax identities."""
+    from kivi_b200 import matmul
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    cache = _mk_cache(B, H, Hkv, kb, vb, g, R, max_tokens=n0 + 64)
+    k = torch.randn((B, Hkv, n0, 128), generator=gen, device="cuda", dtype=torch.float16)
+    v = torch.randn((B, Hkv, n0, 128), generator=gen, device="cuda", dtype=torch.float16)
+    cache.prefill(0, k, v)
+    del k, v
+    tup = cache.export(0)
+    q = (torch.randn((B, H, 128), generator=gen, device="cuda", dtype=torch.float32) * 0.5).half()
+    kn = torch.randn((B, Hkv, 128), generator=gen, device="cuda", dtype=torch.float16)
+    vn = torch.randn((B, Hkv, 128), generator=gen, device="cuda", dtype=torch.float16)
+    T = n0 + 1
+    dbg_s = torch.zeros((B, H, T + 8), dtype=torch.float16, device="cuda")
+    dbg_p = torch.zeros_like(dbg_s)
+    out = cache.decode_attention(0, q, kn, vn, dbg_logits=dbg_s, dbg_probs=dbg_p)
+    out2 = cache.decode_attention(0, q, kn, vn)                     # same state (no advance): the fast path, same result
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2), "debug and fast paths disagree"
+    tk, tv, L = cache.tk, cache.tv, cache.L
+    psum = dbg_p[..., :T].float().sum(-1)
+    assert bool(((psum - 1).abs() < 2e-2).all())
+    lq = matmul.cuda_bmm_fA_qB_outer(g, q[:, :, None, :], tup[0], tup[2], tup[3], kb)[:, :, 0]
+    s_generic = (lq.float() * (1.0 / 11.313708)).half()
+    diff = (dbg_s[..., :tk].float() - s_generic.float()).abs()
+    assert bool((diff <= 1e-3 * s_generic.float().abs() + 2e-3).all()), float(diff.max())
+    # softmax of the kernel's own logits
+    p_ref = torch.softmax(dbg_s[..., :T].float(), -1)
+    assert bool(((dbg_p[..., :T].float() - p_ref).abs() <= 2e-3 * p_ref + 1e-6).all())
+    oq = matmul.cuda_bmm_fA_qB_outer(g, dbg_p[:, :, None, :tv], tup[4], tup[6], tup[7], vb)[:, :, 0]
+    rep = H // Hkv
+    vfull = torch.cat([tup[5], vn[:, :, None, :]], dim=2).repeat_interleave(rep, dim=1)
+    orr = torch.matmul(dbg_p[:, :, None, tv:T].float(), vfull.float())[:, :, 0].half()
+    exp = (oq + orr)
+    d2 = (out.float() - exp.float()).abs()
+    assert bool((d2 <= 2e-3 * exp.float().abs() + 2e-4).all()), float(d2.max())
