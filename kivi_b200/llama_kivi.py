@@ -363,9 +363,12 @@ class LlamaForCausalLM_KIVI(nn.Module):
         cfg, dev, B = self.config, self.cache.device, self.cache.batch
         H, Hkv, hid, inter = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.hidden_size, cfg.intermediate_size
         f = SimpleNamespace(B=B)
-        f.wqkv = [torch.cat([l.self_attn.q_proj.weight, l.self_attn.k_proj.weight, l.self_attn.v_proj.weight], 0).contiguous()
+        # decode-time copies in [in, out] layout: at M = B rows cuBLAS streams the weights 9-13 % faster from this layout
+        # (tools/gemm_probe.py: q|k|v 27.6 vs 31.8 us, o 15.4 vs 17.4 us, gate|up 42.0 vs 46.1 us; down is layout-neutral)
+        f.wqkv = [torch.cat([l.self_attn.q_proj.weight, l.self_attn.k_proj.weight, l.self_attn.v_proj.weight], 0).t().contiguous()
                   for l in self.model.layers]
-        f.wgu = [torch.cat([l.mlp.gate_proj.weight, l.mlp.up_proj.weight], 0).contiguous() for l in self.model.layers]
+        f.wgu = [torch.cat([l.mlp.gate_proj.weight, l.mlp.up_proj.weight], 0).t().contiguous() for l in self.model.layers]
+        f.wo = [l.self_attn.o_proj.weight.t().contiguous() for l in self.model.layers]
         e = lambda *shape: torch.empty(shape, dtype=torch.float16, device=dev)  # noqa: E731
         f.res, f.h, f.o, f.d = e(B, hid), e(B, hid), e(B, hid), e(B, hid)
         f.qkv, f.q, f.k, f.v = e(B, (H + 2 * Hkv) * 128), e(B, H, 128), e(B, Hkv, 128), e(B, Hkv, 128)
@@ -386,12 +389,12 @@ class LlamaForCausalLM_KIVI(nn.Module):
         f.res.copy_(self.model.embed_tokens(self._ids)[:, 0])
         glue.add_rmsnorm(None, f.res, layers[0].input_layernorm.weight, f.h, eps)
         for i, l in enumerate(layers):
-            torch.mm(f.h, f.wqkv[i].t(), out=f.qkv)
+            torch.mm(f.h, f.wqkv[i], out=f.qkv)
             glue.rope_split(f.qkv, cos_t, sin_t, self._pos, f.q, f.k, f.v)
             cache.decode_attention(i, f.q, f.k, f.v, out=f.attn)
-            torch.mm(f.attn.view(f.B, -1), l.self_attn.o_proj.weight.t(), out=f.o)
+            torch.mm(f.attn.view(f.B, -1), f.wo[i], out=f.o)
             glue.add_rmsnorm(f.o, f.res, l.post_attention_layernorm.weight, f.h, eps)
-            torch.mm(f.h, f.wgu[i].t(), out=f.gu)
+            torch.mm(f.h, f.wgu[i], out=f.gu)
             glue.silu_mul(f.gu, f.act)
             torch.mm(f.act, l.mlp.down_proj.weight.t(), out=f.d)
             nxt = layers[i + 1].input_layernorm.weight if i + 1 < len(layers) else self.model.norm.weight
