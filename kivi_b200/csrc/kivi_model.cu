@@ -73,6 +73,9 @@ rope_split_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos
                   int H, int Hkv)
 {
     constexpr int D = 128;
+    // the q.K^T kernel that follows is launched with programmatic serialization: let it set up and start streaming K blocks
+    // while this kernel runs (it waits for our completion before it reads q / k / v)
+    asm volatile("griddepcontrol.launch_dependents;");
     const int b = blockIdx.y, head = blockIdx.x, i = threadIdx.x;            // i < 64: pair (i, i + 64)
     const __half* src = qkv + ((int64_t)b * (H + 2 * Hkv) + head) * D;
     if (head >= H + Hkv) {                                                   // v: plain copy
