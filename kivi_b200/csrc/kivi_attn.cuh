@@ -343,17 +343,28 @@ __device__ __forceinline__ float q_code(float x, float mnf, float scf, float max
 // cache data movement of one unit (models/llama_kivi.py:343-356, :386-399), executed by ONE warp (the last
 // arriver of the unit); cold path, kept out of line.  scratch: 128 bytes of shared memory private to the warp.
 // ------------------------------------------------------------------------------------------------
+// the inputs of a unit's cache update: fetched before the warp's arrival for the unit, so that their round trip overlaps the
+// arrival's (under load a dependent global round trip costs ~2 us and the finalisation sits at the very end of a warp's range)
+struct CommitIn { uint4 vnew4, knew4; uint2 vold; };
+
+__device__ __forceinline__ CommitIn commit_fetch(const AttnParams& p, const Sched& s, int u, int lane)
+{
+    const CacheDesc& c = p.c;
+    CommitIn in;
+    in.vnew4 = make_uint4(0u, 0u, 0u, 0u); in.knew4 = in.vnew4; in.vold = make_uint2(0u, 0u);
+    if (lane < kD / 8) in.vnew4 = __ldg(reinterpret_cast<const uint4*>(p.v_new + (int64_t)u * kD) + lane);
+    if (lane >= 16) in.knew4 = __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (lane - 16));
+    if (s.L + 1 > c.R) in.vold = __ldcg(reinterpret_cast<const uint2*>(c.v_res + (int64_t)u * c.v_res_cap * kD + win_off(s.vhead, lane * 4)));
+    return in;
+}
+
 template <int KB, int VB>
-__device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, int u, int lane, uint8_t* scratch)
+__device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, int u, int lane, uint8_t* scratch, const CommitIn& in)
 {
     const CacheDesc& c = p.c;
     const int g = c.g;
-    // every input is loaded up front: the loads are independent, and under load a dependent global round trip costs ~2 us
-    uint4 vnew4 = make_uint4(0u, 0u, 0u, 0u), knew4 = make_uint4(0u, 0u, 0u, 0u);
-    uint2 vold = make_uint2(0u, 0u);
-    if (lane < kD / 8) vnew4 = __ldg(reinterpret_cast<const uint4*>(p.v_new + (int64_t)u * kD) + lane);
-    if (lane >= 16) knew4 = __ldg(reinterpret_cast<const uint4*>(p.k_new + (int64_t)u * kD) + (lane - 16));
-    if (s.L + 1 > c.R) vold = __ldcg(reinterpret_cast<const uint2*>(c.v_res + (int64_t)u * c.v_res_cap * kD + win_off(s.vhead, lane * 4)));
+    const uint4 vnew4 = in.vnew4, knew4 = in.knew4;
+    const uint2 vold = in.vold;
     // ---- V: v_new joins the ring; if the window would exceed R, its oldest token is quantised per token
     if (lane < kD / 8)                                                                  // window rows are unit-swizzled (win_unit)
         reinterpret_cast<uint4*>(c.v_res + (int64_t)u * c.v_res_cap * kD)[win_unit((s.vhead + s.L) % c.v_res_cap, lane)] = vnew4;
@@ -904,11 +915,12 @@ sv_kernel(const AttnParams p)
     };
     fetch_stats(unit);
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
+    CommitIn pend_cin;
     // The last warp to arrive for a unit adds the records in range order, rounds, writes the output, updates the cache.
-    auto finish_unit = [&](int un, int nparts) {
+    auto finish_unit = [&](int un, int nparts, const CommitIn& cin) {
         const int u = p.hchunks == 1 ? un : un / p.hchunks, hc = p.hchunks == 1 ? 0 : un % p.hchunks;
         const int uq0 = u * ratio + hc * G;
-        __threadfence();                                                     // acquire the other warps' records
+        __syncwarp();                                                        // lane 0's acq_rel arrival covers the other lanes' reads
         if (nparts > 1 && lane == 0) p.w.count[un] = 0;
         float qs[G][4], rs[G][4];
         #pragma unroll
@@ -949,7 +961,7 @@ sv_kernel(const AttnParams p)
             }
             *reinterpret_cast<uint2*>(p.out + (int64_t)(uq0 + h) * kD + lane * 4) = *reinterpret_cast<const uint2*>(o4);
         }
-        if (hc == 0) commit_unit<KB, VB>(p, s, u, lane, scratch);
+        if (hc == 0) commit_unit<KB, VB>(p, s, u, lane, scratch, cin);
     };
     #pragma unroll 1
     while (left > 0) {
@@ -1130,22 +1142,25 @@ sv_kernel(const AttnParams p)
                 *reinterpret_cast<float4*>(recp + (h * 2 + 1) * kD + lane * 4) = make_float4(orr[h][0], orr[h][1], orr[h][2], orr[h][3]);
         }
         // the arrival of the PREVIOUS unit has had a whole unit's time to return: finalise it if this warp was its last
-        if (pend_unit >= 0 && __shfl_sync(0xffffffffu, pend_old, 0) == pend_nparts - 1) finish_unit(pend_unit, pend_nparts);
+        if (pend_unit >= 0 && __shfl_sync(0xffffffffu, pend_old, 0) == pend_nparts - 1) finish_unit(pend_unit, pend_nparts, pend_cin);
         pend_unit = -1;
-        // arrive: the records of all lanes happen-before lane 0's release (__syncwarp); the counter's old value is not
-        // needed before the next unit is done, so its round trip to L2 is off the critical path
+        // the inputs of this unit's cache update travel together with the arrival below
+        pend_cin = commit_fetch(p, s, u, lane);
+        // arrive: the records of all lanes happen-before lane 0's release (__syncwarp), and its acquire makes the records of
+        // the earlier arrivals visible to a last arriver; the counter's old value is not needed before the next unit is
+        // done, so its round trip to L2 is off the critical path
         __syncwarp();
         if (nparts > 1) {
             if (lane == 0)
-                asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + unit) : "memory");
+                asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + unit) : "memory");
             pend_unit = unit; pend_nparts = nparts;
         } else {
-            finish_unit(unit, 1);                                            // the whole unit was this warp's
+            finish_unit(unit, 1, pend_cin);                                  // the whole unit was this warp's
         }
         left -= n_here;
         if (j == s.bpu) { j = 0; ++unit; }
     }
-    if (pend_unit >= 0 && __shfl_sync(0xffffffffu, pend_old, 0) == pend_nparts - 1) finish_unit(pend_unit, pend_nparts);
+    if (pend_unit >= 0 && __shfl_sync(0xffffffffu, pend_old, 0) == pend_nparts - 1) finish_unit(pend_unit, pend_nparts, pend_cin);
 }
 
 // ------------------------------------------------------------------------------------------------
