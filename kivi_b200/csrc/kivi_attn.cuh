@@ -78,6 +78,15 @@ constexpr float kProbScale = 64.f, kProbScaleInv = 1.f / 64.f;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 
+#if KIVI_TIMELINE
+// per-warp timestamps (globaltimer ns) of the two kernels: [kernel][warp][entry, first data, blocks done, exit, smid]
+static __device__ unsigned long long g_timeline[2][4096][8];   // one copy per translation unit
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define KIVI_TL(k, w, i) do { if (lane == 0 && (w) < 4096) { g_timeline[k][w][i] = gtime(); if ((i) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_timeline[k][w][4] = sm_; } } } while (0)
+#else
+#define KIVI_TL(k, w, i) do {} while (0)
+#endif
+
 struct Workspace {                     // carved from the caller's buffer (kivi_decode_workspace_bytes)
     __half* lg; long long ld;          // [B*H][ld] scaled logits (fp16), ld % 128 == 0
     float2* stats; int stat_cap;       // [B*H][stat_cap] (max, sum exp(x - max)) per qk item
@@ -598,6 +607,7 @@ qk_kernel(const AttnParams p)
     const Sched s = make_sched(c);
     const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
+    KIVI_TL(0, gw, 0);
     const long long N = (long long)p.n_units * s.ipu;                        // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);
     if (gw >= W) return;
@@ -629,6 +639,7 @@ qk_kernel(const AttnParams p)
     };
     pdl_wait();                                                              // q / k_new come from the previous kernel of the stream
     fetch_q(unit);
+    KIVI_TL(0, gw, 1);
     #pragma unroll 1
     while (left > 0) {
         const int u = p.hchunks == 1 ? unit : unit / p.hchunks, hc = p.hchunks == 1 ? 0 : unit % p.hchunks;
@@ -798,6 +809,7 @@ qk_kernel(const AttnParams p)
         left -= n_here;
         if (j == s.ipu) { j = 0; ++unit; }
     }
+    KIVI_TL(0, gw, 3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -879,6 +891,7 @@ sv_kernel(const AttnParams p)
     const Sched s = make_sched(c);
     const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
+    KIVI_TL(1, gw, 0);
     const long long N = (long long)p.n_units * s.bpu;                       // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);                        // range owners: every range is non-empty
     if (gw >= W) return;
@@ -914,6 +927,7 @@ sv_kernel(const AttnParams p)
         }
     };
     fetch_stats(unit);
+    KIVI_TL(1, gw, 1);
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
     CommitIn pend_cin;
     // The last warp to arrive for a unit adds the records in range order, rounds, writes the output, updates the cache.
@@ -1160,7 +1174,9 @@ sv_kernel(const AttnParams p)
         left -= n_here;
         if (j == s.bpu) { j = 0; ++unit; }
     }
+    KIVI_TL(1, gw, 2);
     if (pend_unit >= 0 && __shfl_sync(0xffffffffu, pend_old, 0) == pend_nparts - 1) finish_unit(pend_unit, pend_nparts, pend_cin);
+    KIVI_TL(1, gw, 3);
 }
 
 // ------------------------------------------------------------------------------------------------
