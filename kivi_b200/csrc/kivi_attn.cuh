@@ -57,7 +57,13 @@ namespace kivi {
 
 int make_desc(const kivi_cache_t* k, CacheDesc* d);
 
-constexpr int kCW = 8;                 // warps per CTA (they never synchronise with each other)
+// Warps per CTA (they never synchronise with each other).  16 = ONE CTA per SM: with two CTAs of 8 warps the SM's warp
+// scheduler favours the older CTA, whose warps finish ~25 % earlier and leave the SM half empty for the last ~10 us of a
+// 50 us kernel (tools/timeline.py, profiles/r01_timeline_static_ranges.txt); sixteen warps of one age finish together.
+#ifndef KIVI_CW
+#define KIVI_CW 16
+#endif
+constexpr int kCW = KIVI_CW;
 constexpr int kThreads = kCW * 32;
 // A pipeline stage holds kHalfChunks of the 8 chunks (16 inner indices each) of a packed block: 8 = whole blocks
 // (one 6 KB bulk copy), 4 = half blocks.  Measured (tools/sweep_occupancy.sh, profiles/): half blocks allow 3 CTAs
@@ -584,7 +590,7 @@ __device__ __forceinline__ void qk_issue_next(Pipe& pp, Cursor& cur, const AttnP
 }
 
 template <int KB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, (G == 1 && kParts > 1) ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, kCW >= 16 ? 1 : 2)
 qk_kernel(const AttnParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -869,7 +875,7 @@ __device__ __forceinline__ float prob_f32(float x, float M, float S, float rS) {
 }
 
 template <int KB, int VB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, (G == 1 && kParts > 1) ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, kCW >= 16 ? 1 : 2)
 sv_kernel(const AttnParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1193,7 +1199,7 @@ static inline void query_device() {
     }
 }
 
-constexpr int kMaxCtasPerSm = kParts == 1 ? 2 : 3;
+constexpr int kMaxCtasPerSm = kCW >= 16 ? 1 : 2;
 
 // workspace carve-up (shared by kivi_decode_workspace_bytes and the launcher)
 static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, int max_kv_len, void* base, Workspace* w)
@@ -1231,7 +1237,7 @@ static int launch_attention(AttnParams& p, cudaStream_t st)
     const int stage = max(max(half_k, half_v), kResBytes);
     p.stage_bytes = (stage + 127) / 128 * 128;
     const int fixed = 512 + kCW * G * (32 * 8 + kD * 4);                     // barriers + per-warp q buffers (qk) / window outputs (sv)
-    int ctas = G == 1 ? kMaxCtasPerSm : 2;                                   // the kernels' __launch_bounds__
+    int ctas = kMaxCtasPerSm;                                                // the kernels' __launch_bounds__
     p.spw = 0;
     for (; ctas >= 1; --ctas) {                                              // most CTAs per SM that still get >= 2 stages per warp
         p.spw = min(4, (g_max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));

@@ -35,7 +35,7 @@ fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p]
 assert fn(buf.ctypes.data) == 0
 os.makedirs('gpurun_out', exist_ok=True)
-np.save('gpurun_out/timeline.npy', buf)
+np.save(os.environ.get('KIVI_TL_OUT', 'gpurun_out/timeline.npy'), buf)
 t0 = buf[0][:, 0][buf[0][:, 0] > 0].min()
 for kname, kk, cols in (("qk", 0, (0, 1, 3)), ("sv", 1, (0, 1, 2, 3))):
     a = buf[kk]
