@@ -89,6 +89,11 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 static __device__ unsigned long long g_timeline[2][4096][8];   // one copy per translation unit
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define KIVI_TL(k, w, i) do { if (lane == 0 && (w) < 4096) { g_timeline[k][w][i] = gtime(); if ((i) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_timeline[k][w][4] = sm_; } } } while (0)
+// every translation unit has its own copy (no relocatable device code), and a kernel instantiated in two of them (the
+// q.K^T kernel does not depend on v_bits) writes whichever copy the linker kept: kivi_debug_timeline merges all of them
+static inline int timeline_fetch(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 2 * 4096 * 8);
+}
 #else
 #define KIVI_TL(k, w, i) do {} while (0)
 #endif

@@ -8,9 +8,5 @@ int64_t workspace_k2v2(const CacheDesc& c, int n_units, int G, int max_kv_len, v
 }
 
 #if KIVI_TIMELINE
-// tuning builds only (tools/timeline.py): the per-warp timestamps of the last k2v2 attention call
-extern "C" int kivi_debug_timeline(unsigned long long* host_out)
-{
-    return (int)cudaMemcpyFromSymbol(host_out, kivi::g_timeline, sizeof(unsigned long long) * 2 * 4096 * 8);
-}
+namespace kivi { int timeline_k2v2(unsigned long long* host_out) { return timeline_fetch(host_out); } }   // tuning builds (tools/timeline.py)
 #endif

@@ -6,3 +6,7 @@ int64_t workspace_k2v4(const CacheDesc& c, int n_units, int G, int max_kv_len, v
     return carve_workspace(c, n_units, G, max_kv_len, base, w);
 }
 }
+
+#if KIVI_TIMELINE
+namespace kivi { int timeline_k2v4(unsigned long long* host_out) { return timeline_fetch(host_out); } }   // tuning builds (tools/timeline.py)
+#endif

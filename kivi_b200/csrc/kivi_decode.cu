@@ -53,3 +53,25 @@ extern "C" int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* 
     if (p.c.k_bits == 4 && p.c.v_bits == 2) return attention_k4v2(p, G, st);
     return KIVI_ERR_BITS;
 }
+
+#if KIVI_TIMELINE
+#include <vector>
+namespace kivi {
+int timeline_k2v2(unsigned long long*); int timeline_k2v4(unsigned long long*);
+int timeline_k4v2(unsigned long long*); int timeline_k4v4(unsigned long long*);
+}
+// tuning builds only (tools/timeline.py): the per-warp timestamps of the last attention call, [2][4096][8]
+extern "C" int kivi_debug_timeline(unsigned long long* host_out)
+{
+    const size_t n = 2 * 4096 * 8;
+    std::vector<unsigned long long> tmp(n);
+    for (size_t i = 0; i < n; ++i) host_out[i] = 0;
+    int (*fetch[4])(unsigned long long*) = {timeline_k2v2, timeline_k2v4, timeline_k4v2, timeline_k4v4};
+    for (auto f : fetch) {
+        const int rc = f(tmp.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < n; ++i) if (tmp[i] > host_out[i]) host_out[i] = tmp[i];   // timestamps: the latest writer wins
+    }
+    return 0;
+}
+#endif
