@@ -129,13 +129,21 @@ int kivi_unpack_dequant_lastdim_f16(const void* code, const void* scale, const v
  * head_dim is 128 (every model the reference ships); group_size in {32,64,128};
  * residual_length % group_size == 0 (:344), residual_length in {32, 64, 128, 256}.
  * ========================================================================================== */
+/* kivi_cache_t.flags.  KIVI_CACHE_OVERLAP_PROLOGUE: the caller promises that the kernel enqueued on the stream
+ * directly before kivi_decode_attention_f16 never writes this cache (stores, windows) or its `state` -- true inside a
+ * decoder layer, where that kernel produces q / k_new / v_new.  The q.K^T launch then starts under programmatic
+ * dependent launch: it reads `state` and its first K blocks while that kernel drains, and waits for it only before
+ * touching q / k_new.  Without the flag the q.K^T kernel is an ordinary launch (safe directly after
+ * kivi_cache_advance / kivi_cache_prefill_f16 / a previous attention call on the same cache). */
+#define KIVI_CACHE_OVERLAP_PROLOGUE 1
+
 typedef struct kivi_cache {
     int32_t batch, num_heads, num_kv_heads, head_dim;
     int32_t k_bits, v_bits, group_size, residual_length;
     int32_t k_cap_blocks;   /* capacity of the K store in 128-token blocks   (kivi_cache_sizes out[0]) */
     int32_t v_cap_blocks;   /* capacity of the V store in 128-token blocks   (out[1]) */
     int32_t v_res_cap;      /* slots of the fp16 V ring buffer               (out[2]) */
-    int32_t reserved;
+    int32_t flags;          /* KIVI_CACHE_* bits, 0 = none */
     void* k_store;          /* out[3] bytes */
     void* v_store;          /* out[4] bytes */
     void* k_res;            /* out[5] bytes */
@@ -178,14 +186,16 @@ int64_t kivi_decode_workspace_bytes(const kivi_cache_t* cache, int max_kv_len);
  *   statistics, partial output records, arrival counters); no bound on the context length
  *   dbg_logits / dbg_probs: NULL or fp16 [B, H, dbg_stride] receiving s and p (tests)
  *   max_kv_len: the value the workspace was sized with (>= kv_len + 1).
- * Two launches on `stream`, no CTA barrier in either: every warp of a persistent grid is an autonomous worker
- * that streams 128-token packed blocks HBM -> shared memory with cp.async.bulk (TMA) into private mbarrier
- * stages.  (1) q.K^T: items dealt round-robin; each writes its fp16 logits and (max, sum exp) statistics.
- * (2) p.V: the (unit, block) sequence is cut into one contiguous range per warp; a warp normalises its logits
- * slices with the row's combined statistics, accumulates, and writes one partial record per unit; the last
- * arriver of a unit adds the records in fixed order, rounds, writes `out` and updates the cache.  The
- * contraction of a packed block runs on mma.sync (codes as exact fp16 denormals x exact hi/lo split of
- * x*scale, fp32 accumulate); the query heads of a KV head share the MMAs (GQA). */
+ * Two launches on `stream`, no CTA barrier in either: every warp of a persistent grid (one 16-warp CTA per SM) is an
+ * autonomous worker that owns one contiguous range of the (unit, 128-token block) sequence and streams its packed
+ * blocks HBM -> shared memory with cp.async.bulk (TMA) into private mbarrier stages.  (1) q.K^T: a warp writes the
+ * fp16 logits of its blocks and one (max, sum exp) pair per unit it touches.  (2) p.V (programmatic dependent launch
+ * on (1)): a warp normalises its logits slices with the unit's combined statistics, accumulates, and writes one
+ * partial record per unit; the last arriver of a unit adds the records in fixed order, rounds, writes `out` and
+ * updates the cache.  The contraction of a packed block runs on mma.sync (codes as exact fp16 denormals x exact
+ * hi/lo split of x*scale, fp32 accumulate); the query heads of a KV head share the MMAs (GQA).
+ * Launch (1) reads `state` and its first K blocks at once: it is an ordinary launch unless cache->flags has
+ * KIVI_CACHE_OVERLAP_PROLOGUE (see there). */
 int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const void* k_new, const void* v_new,
                               const void* mask, void* out, void* workspace, int64_t workspace_bytes,
                               void* dbg_logits, void* dbg_probs, int64_t dbg_stride, int max_kv_len, void* stream);

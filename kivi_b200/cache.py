@@ -18,7 +18,7 @@ class _CacheStruct(ctypes.Structure):
     """kivi_cache_t of include/kivi_b200.h"""
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("batch", "num_heads", "num_kv_heads", "head_dim", "k_bits", "v_bits", "group_size",
-                 "residual_length", "k_cap_blocks", "v_cap_blocks", "v_res_cap", "reserved")] + \
+                 "residual_length", "k_cap_blocks", "v_cap_blocks", "v_res_cap", "flags")] + \
                [(n, ctypes.c_void_p) for n in ("k_store", "v_store", "k_res", "v_res", "state")]
 
 
@@ -45,7 +45,10 @@ class KiviCache:
 
     def __init__(self, n_layers: int, batch: int, num_heads: int, num_kv_heads: int, head_dim: int = 128,
                  k_bits: int = 2, v_bits: int = 2, group_size: int = 32, residual_length: int = 128,
-                 max_tokens: int = 4096, device="cuda"):
+                 max_tokens: int = 4096, device="cuda", overlap_prologue: bool = False):
+        """overlap_prologue = KIVI_CACHE_OVERLAP_PROLOGUE of include/kivi_b200.h: promise that the kernel enqueued directly
+        before every decode_attention() call never writes this cache (true inside a decoder layer, where it produces
+        q / k_new / v_new), so the q.K^T launch may overlap its tail."""
         _bind()
         if head_dim != 128:
             raise NotImplementedError("kivi_b200 fused decode supports head_dim 128 (all models the reference ships)")
@@ -65,7 +68,7 @@ class KiviCache:
         for _ in range(n_layers):
             bufs = [torch.zeros(nb, dtype=torch.uint8, device=self.device) for nb in self._bytes]
             st = _CacheStruct(batch, num_heads, num_kv_heads, head_dim, k_bits, v_bits, group_size, residual_length,
-                              self.k_cap_blocks, self.v_cap_blocks, self.v_res_cap, 0,
+                              self.k_cap_blocks, self.v_cap_blocks, self.v_res_cap, 1 if overlap_prologue else 0,
                               *[b.data_ptr() for b in bufs], self.state.data_ptr())
             self._bufs.append(bufs)
             self._structs.append(st)

@@ -1233,7 +1233,7 @@ static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, in
 }
 
 template <int KB, int VB, int G, int GS>
-static int launch_attention(AttnParams& p, cudaStream_t st)
+static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t st)
 {
     const CacheDesc& c = p.c;
     query_device();
@@ -1270,30 +1270,34 @@ static int launch_attention(AttnParams& p, cudaStream_t st)
     // ranges per unit than the workspace has record / statistics slots: part_cap - 2 warps per unit at most
     const long long want = (long long)p.n_units * max(1, p.w.part_cap - 2);
     p.nw_eff = (int)min((long long)grid * kCW, want);
-    // both launches carry the programmatic-serialization attribute: the q.K^T prologue (setup, state, first K blocks in
-    // flight) overlaps the tail of the previous kernel of the stream, the p.V prologue overlaps the q.K^T tail
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = getenv("KIVI_NO_PDL") ? 0 : 1;
+    // programmatic dependent launch: the p.V prologue (setup, cache lengths) overlaps the q.K^T tail; the q.K^T prologue
+    // (setup, lengths, first K blocks in flight) overlaps the tail of the previous kernel of the stream only when the
+    // caller has promised that that kernel does not write the cache (KIVI_CACHE_OVERLAP_PROLOGUE)
+    const bool pdl = getenv("KIVI_NO_PDL") == nullptr;
+    cudaLaunchAttribute attr_qk[1], attr_sv[1];
+    attr_qk[0].id = attr_sv[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr_qk[0].val.programmaticStreamSerializationAllowed = pdl && overlap_prologue ? 1 : 0;
+    attr_sv[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr_qk; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kqk, p);
     if (e != cudaSuccess) return (int)e;
     int rc = post_launch(); if (rc) return rc;
+    cfg.attrs = attr_sv;
     e = cudaLaunchKernelEx(&cfg, ksv, p);
     if (e != cudaSuccess) return (int)e;
     return post_launch();
 }
 
 template <int KB, int VB>
-static int dispatch_attention(AttnParams& p, int G, cudaStream_t st)
+static int dispatch_attention(AttnParams& p, int G, bool overlap_prologue, cudaStream_t st)
 {
     #define KIVI_GS(GS_)                                                                  \
         if (p.c.g == GS_) {                                                               \
-            if (G == 4) return launch_attention<KB, VB, 4, GS_>(p, st);                   \
-            if (G == 2) return launch_attention<KB, VB, 2, GS_>(p, st);                   \
-            return launch_attention<KB, VB, 1, GS_>(p, st);                               \
+            if (G == 4) return launch_attention<KB, VB, 4, GS_>(p, overlap_prologue, st);                   \
+            if (G == 2) return launch_attention<KB, VB, 2, GS_>(p, overlap_prologue, st);                   \
+            return launch_attention<KB, VB, 1, GS_>(p, overlap_prologue, st);                               \
         }
     KIVI_GS(32)
     KIVI_GS(64)

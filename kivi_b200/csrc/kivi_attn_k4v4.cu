@@ -1,7 +1,7 @@
 // instantiation of the decode attention kernels for k_bits = 4, v_bits = 4 (all G, all group sizes)
 #include "kivi_attn.cuh"
 namespace kivi {
-int attention_k4v4(AttnParams& p, int G, cudaStream_t st) { return dispatch_attention<4, 4>(p, G, st); }
+int attention_k4v4(AttnParams& p, int G, bool overlap_prologue, cudaStream_t st) { return dispatch_attention<4, 4>(p, G, overlap_prologue, st); }
 int64_t workspace_k4v4(const CacheDesc& c, int n_units, int G, int max_kv_len, void* base, Workspace* w) {
     return carve_workspace(c, n_units, G, max_kv_len, base, w);
 }

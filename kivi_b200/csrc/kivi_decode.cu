@@ -4,10 +4,10 @@
 #include "kivi_attn.cuh"
 
 namespace kivi {
-int attention_k2v2(AttnParams& p, int G, cudaStream_t st);
-int attention_k4v4(AttnParams& p, int G, cudaStream_t st);
-int attention_k2v4(AttnParams& p, int G, cudaStream_t st);
-int attention_k4v2(AttnParams& p, int G, cudaStream_t st);
+int attention_k2v2(AttnParams& p, int G, bool overlap_prologue, cudaStream_t st);
+int attention_k4v4(AttnParams& p, int G, bool overlap_prologue, cudaStream_t st);
+int attention_k2v4(AttnParams& p, int G, bool overlap_prologue, cudaStream_t st);
+int attention_k4v2(AttnParams& p, int G, bool overlap_prologue, cudaStream_t st);
 }
 
 using namespace kivi;
@@ -41,16 +41,17 @@ extern "C" int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* 
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return KIVI_ERR_ALIGN;
     p.q = (const __half*)q; p.k_new = (const __half*)k_new; p.v_new = (const __half*)v_new; p.mask = (const __half*)mask;
     p.out = (__half*)out; p.dbg_logits = (__half*)dbg_logits; p.dbg_probs = (__half*)dbg_probs; p.dbg_stride = dbg_stride;
+    const bool overlap = (cache->flags & KIVI_CACHE_OVERLAP_PROLOGUE) != 0;   // the q.K^T launch may overlap its predecessor
     const int ratio = p.c.H / p.c.Hkv;
     const int G = gqa_chunk(ratio);
     p.hchunks = ratio / G;
     p.n_units = p.c.B * p.c.Hkv * p.hchunks;
     if (carve_workspace(p.c, p.n_units, G, max_kv_len, workspace, &p.w) > workspace_bytes) return KIVI_ERR_CAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
-    if (p.c.k_bits == 2 && p.c.v_bits == 2) return attention_k2v2(p, G, st);
-    if (p.c.k_bits == 4 && p.c.v_bits == 4) return attention_k4v4(p, G, st);
-    if (p.c.k_bits == 2 && p.c.v_bits == 4) return attention_k2v4(p, G, st);
-    if (p.c.k_bits == 4 && p.c.v_bits == 2) return attention_k4v2(p, G, st);
+    if (p.c.k_bits == 2 && p.c.v_bits == 2) return attention_k2v2(p, G, overlap, st);
+    if (p.c.k_bits == 4 && p.c.v_bits == 4) return attention_k4v4(p, G, overlap, st);
+    if (p.c.k_bits == 2 && p.c.v_bits == 4) return attention_k2v4(p, G, overlap, st);
+    if (p.c.k_bits == 4 && p.c.v_bits == 2) return attention_k4v2(p, G, overlap, st);
     return KIVI_ERR_BITS;
 }
 

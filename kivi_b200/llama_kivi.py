@@ -311,7 +311,8 @@ class LlamaForCausalLM_KIVI(nn.Module):
         dev = self.lm_head.weight.device
         self.cache = KiviCache(cfg.num_hidden_layers, batch, cfg.num_attention_heads, cfg.num_key_value_heads,
                                cfg.hidden_size // cfg.num_attention_heads, cfg.k_bits, cfg.v_bits, cfg.group_size,
-                               cfg.residual_length, max_tokens, device=dev)
+                               cfg.residual_length, max_tokens, device=dev,
+                               overlap_prologue=True)       # the attention call follows the layer's RoPE kernel
         self._graph = None
         self._pos = torch.zeros((batch, 1), dtype=torch.long, device=dev)
         self._ids = torch.zeros((batch, 1), dtype=torch.long, device=dev)

@@ -20,7 +20,9 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--mode", default="fused")
 a = ap.parse_args()
 gen = torch.Generator(device="cuda").manual_seed(0)
-cache = KiviCache(1, a.B, a.H, a.Hkv, 128, a.bits, a.bits, a.g, a.R, max_tokens=a.n + 256)
+# launched as inside a decoder layer (the q.K^T prologue may overlap the previous kernel: results are not checked here)
+cache = KiviCache(1, a.B, a.H, a.Hkv, 128, a.bits, a.bits, a.g, a.R, max_tokens=a.n + 256,
+                  overlap_prologue=True)
 k = torch.randn((a.B, a.Hkv, a.n, 128), generator=gen, device="cuda", dtype=torch.float16)
 v = torch.randn((a.B, a.Hkv, a.n, 128), generator=gen, device="cuda", dtype=torch.float16)
 cache.prefill(0, k, v)

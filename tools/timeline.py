@@ -15,7 +15,9 @@ from kivi_b200.cache import KiviCache  # noqa: E402
 
 B, H, Hkv, n = 32, 32, 32, 4032
 gen = torch.Generator(device="cuda").manual_seed(0)
-cache = KiviCache(1, B, H, Hkv, 128, 2, 2, 32, 128, max_tokens=n + 256)
+# launched as inside a decoder layer (the q.K^T prologue may overlap the previous kernel: results are not checked here)
+cache = KiviCache(1, B, H, Hkv, 128, 2, 2, 32, 128, max_tokens=n + 256,
+                  overlap_prologue=True)
 k = torch.randn((B, Hkv, n, 128), generator=gen, device="cuda", dtype=torch.float16)
 v = torch.randn((B, Hkv, n, 128), generator=gen, device="cuda", dtype=torch.float16)
 cache.prefill(0, k, v)
