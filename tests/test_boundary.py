@@ -112,3 +112,27 @@ def test_cpu_tensors_are_rejected():
                                     torch.zeros((1, 1, 8, 2), dtype=torch.int32),
                                     torch.zeros((1, 1, 8, 1), dtype=torch.float16),
                                     torch.zeros((1, 1, 8, 1), dtype=torch.float16), 2)
+
+
+def test_cache_struct_mirrors_the_header():
+    """kivi_b200.cache._CacheStruct (ctypes) has the fields of kivi_cache_t in include/kivi_b200.h, in order, and the
+    overlap flag the Python side sets is the header's KIVI_CACHE_OVERLAP_PROLOGUE."""
+    import ctypes
+    from kivi_b200 import cache
+    txt = open(os.path.join(ROOT, "include", "kivi_b200.h")).read()
+    body = re.search(r"typedef struct kivi_cache \{(.*?)\} kivi_cache_t;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = ("ptr", decl.replace("void*", "")) if decl.startswith("void*") else ("i32", decl.replace("int32_t", ""))
+        fields += [(n.strip(), ctype) for n in names.split(",")]
+    mirror = [(n, "ptr" if t is ctypes.c_void_p else "i32") for n, t in cache._CacheStruct._fields_]
+    assert mirror == fields
+    assert ctypes.sizeof(cache._CacheStruct) == 12 * 4 + 5 * 8
+    flag = int(re.search(r"#define KIVI_CACHE_OVERLAP_PROLOGUE\s+(\d+)", txt).group(1))
+    assert flag == 1                                                  # KiviCache(overlap_prologue=True) stores 1 in `flags`
+    src = inspect.getsource(cache.KiviCache.__init__)
+    assert "1 if overlap_prologue else 0" in src
