@@ -136,6 +136,11 @@ int kivi_unpack_dequant_lastdim_f16(const void* code, const void* scale, const v
  * touching q / k_new.  Without the flag the q.K^T kernel is an ordinary launch (safe directly after
  * kivi_cache_advance / kivi_cache_prefill_f16 / a previous attention call on the same cache). */
 #define KIVI_CACHE_OVERLAP_PROLOGUE 1
+/* Bits 4..6 of kivi_cache_t.flags: how many query heads of a KV head share one work unit of the decode attention
+ * (their MMAs and every packed byte): 0 = chosen from the geometry (4 if nh/nh_kv % 4 == 0, else 2, else 1), or an
+ * explicit 1 / 2 / 4 dividing nh/nh_kv.  kivi_decode_workspace_bytes and kivi_decode_attention_f16 must see the same value. */
+#define KIVI_CACHE_GQA_CHUNK_SHIFT 4
+#define KIVI_CACHE_GQA_CHUNK(g)    ((g) << KIVI_CACHE_GQA_CHUNK_SHIFT)
 
 typedef struct kivi_cache {
     int32_t batch, num_heads, num_kv_heads, head_dim;
@@ -203,6 +208,12 @@ int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const vo
 /* Advance `state` by one token (the bookkeeping of :343-356, :386-399); once per step, all layers. */
 int kivi_cache_advance(const kivi_cache_t* cache, void* stream);
 
+/* Copy the 8 words of `state` to host memory (synchronises `stream`).  state[6] is an error word that the decode kernels
+ * set instead of touching memory when the device-side lengths exceed what the call declared (max_kv_len, window
+ * capacities): KIVI_STATE_ERR_CAPACITY.  kivi_cache_prefill_f16 / kivi_cache_import_f16 clear it. */
+#define KIVI_STATE_ERR_CAPACITY 1
+int kivi_cache_read_state(const kivi_cache_t* cache, int32_t* host_state8, void* stream);
+
 /* Copy the cache out in the reference's 9-tuple layout (models/llama_kivi.py:454-455); lengths are
  * passed by the host (it mirrors `state`).  k_code [U,128,tk/fpi] i32, k_scale/k_mn [U,128,tk/g],
  * k_full [U,r,128], v_code [U,tv,128/fpi] i32, v_scale/v_mn [U,tv,128/g], v_full [U,L,128]. */
@@ -210,18 +221,28 @@ int kivi_cache_export_f16(const kivi_cache_t* cache, int tk, int r, int tv, int 
                           void* k_code, void* k_scale, void* k_mn, void* k_full,
                           void* v_code, void* v_scale, void* v_mn, void* v_full, void* stream);
 
+/* The inverse of kivi_cache_export_f16: load one layer's cache from the reference's 9-tuple (the object a model that
+ * ran on the reference's hook holds, models/llama_kivi.py:454-455) and set `state` = {tk, r, tv, L, 0, tk + r}.
+ * Same operand shapes as the export; tk % residual_length == 0, r < residual_length, L <= residual_length,
+ * tk + r == tv + L (both count the tokens seen).  Pointers of empty parts (tk == 0, r == 0, tv == 0) may be NULL. */
+int kivi_cache_import_f16(const kivi_cache_t* cache, int tk, int r, int tv, int L,
+                          const void* k_code, const void* k_scale, const void* k_mn, const void* k_full,
+                          const void* v_code, const void* v_scale, const void* v_mn, const void* v_full, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Glue kernels of the decode step around the hot path (not part of the KIVI operators; they
  * replace ~16 ATen elementwise launches per layer per step in kivi_b200/llama_kivi.py).  fp16 I/O,
  * arithmetic of the HF Llama modules the reference forks: every fp16 op rounds to fp16.
  *   kivi_add_rmsnorm_f16 : residual += x (x may be NULL); out = weight * fp16(residual * rsqrt(mean(residual^2)+eps))
- *   kivi_rope_split_f16  : qkv [B,(H+2Hkv)*128] -> q [B,H,128], k [B,Hkv,128] (rotary at position pos[b], int64), v
+ *   kivi_rope_split_f16  : qkv [B,(H+2Hkv)*128] -> q [B,H,128], k [B,Hkv,128] (rotary at position pos[b], int64,
+ *                          clamped to the table_rows rows of the cos / sin tables [table_rows, 128]), v
  *   kivi_silu_mul_f16    : gate_up [rows, 2*I] -> out [rows, I] = fp16(silu(gate)) * up
  * ------------------------------------------------------------------------------------------ */
 int kivi_add_rmsnorm_f16(const void* x, void* residual, const void* weight, void* out,
                          int rows, int hidden, float eps, void* stream);
 int kivi_rope_split_f16(const void* qkv, const void* cos_table, const void* sin_table, const void* pos,
-                        void* q, void* k, void* v, int batch, int num_heads, int num_kv_heads, void* stream);
+                        void* q, void* k, void* v, int batch, int num_heads, int num_kv_heads, int table_rows,
+                        void* stream);
 int kivi_silu_mul_f16(const void* gate_up, void* out, int rows, int intermediate, void* stream);
 
 #ifdef __cplusplus

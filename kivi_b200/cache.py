@@ -37,6 +37,8 @@ def _bind():
     _lib.bind("kivi_decode_attention_f16", i32, [P, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i32, vp])
     _lib.bind("kivi_cache_advance", i32, [P, vp])
     _lib.bind("kivi_cache_export_f16", i32, [P, i32, i32, i32, i32, i32] + [vp] * 9)
+    _lib.bind("kivi_cache_import_f16", i32, [P, i32, i32, i32, i32] + [vp] * 9)
+    _lib.bind("kivi_cache_read_state", i32, [P, ctypes.POINTER(ctypes.c_int32), vp])
     _BOUND = True
 
 
@@ -45,10 +47,11 @@ class KiviCache:
 
     def __init__(self, n_layers: int, batch: int, num_heads: int, num_kv_heads: int, head_dim: int = 128,
                  k_bits: int = 2, v_bits: int = 2, group_size: int = 32, residual_length: int = 128,
-                 max_tokens: int = 4096, device="cuda", overlap_prologue: bool = False):
+                 max_tokens: int = 4096, device="cuda", overlap_prologue: bool = False, gqa_chunk: int = 0):
         """overlap_prologue = KIVI_CACHE_OVERLAP_PROLOGUE of include/kivi_b200.h: promise that the kernel enqueued directly
         before every decode_attention() call never writes this cache (true inside a decoder layer, where it produces
-        q / k_new / v_new), so the q.K^T launch may overlap its tail."""
+        q / k_new / v_new), so the q.K^T launch may overlap its tail.
+        gqa_chunk = KIVI_CACHE_GQA_CHUNK: query heads of a KV head that share one work unit (0 = from the geometry)."""
         _bind()
         if head_dim != 128:
             raise NotImplementedError("kivi_b200 fused decode supports head_dim 128 (all models the reference ships)")
@@ -68,7 +71,8 @@ class KiviCache:
         for _ in range(n_layers):
             bufs = [torch.zeros(nb, dtype=torch.uint8, device=self.device) for nb in self._bytes]
             st = _CacheStruct(batch, num_heads, num_kv_heads, head_dim, k_bits, v_bits, group_size, residual_length,
-                              self.k_cap_blocks, self.v_cap_blocks, self.v_res_cap, 1 if overlap_prologue else 0,
+                              self.k_cap_blocks, self.v_cap_blocks, self.v_res_cap,
+                              (1 if overlap_prologue else 0) | (int(gqa_chunk) << 4),
                               *[b.data_ptr() for b in bufs], self.state.data_ptr())
             self._bufs.append(bufs)
             self._structs.append(st)
@@ -157,6 +161,55 @@ class KiviCache:
             _lib.check(_lib.lib().kivi_cache_advance(ctypes.byref(self._structs[0]), _lib.stream_ptr(self.device)),
                        "kivi_cache_advance")
         self._mirror_advance()
+
+    def read_state(self):
+        """The device-side `state` words (synchronises the stream); raises if a decode kernel flagged a capacity
+        violation (KIVI_STATE_ERR_CAPACITY in state[6]) and checks the host mirror."""
+        host = (ctypes.c_int32 * 8)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().kivi_cache_read_state(ctypes.byref(self._structs[0]), host, _lib.stream_ptr(self.device)),
+                       "kivi_cache_read_state")
+        st = list(host)
+        if st[6] != 0:
+            raise RuntimeError(f"kivi_b200: the decode kernels refused to run (state error word {st[6]}): the device-side "
+                               f"lengths {st[:6]} exceed the capacity the cache was created with")
+        return st
+
+    def import_tuple(self, layer: int, past):
+        """Load `layer` from the reference's per-layer 9-tuple (models/llama_kivi.py:454-455), the inverse of
+        export(): a cache that was built by the reference's own hook (or by kivi_prefill_tuple /
+        kivi_decode_attention_tuple) continues on the fused path.  All layers of a model share one `state`, so every
+        layer must be imported from tuples of the same lengths."""
+        kc, kfull, ks, km, vc, vfull, vs, vm, seen = past
+        B, Hkv, D, g = self.batch, self.num_kv_heads, self.head_dim, self.group_size
+        kf, vf = 32 // self.k_bits, 32 // self.v_bits
+        tk = 0 if kc is None else kc.shape[-1] * kf
+        r = 0 if kfull is None else kfull.shape[-2]
+        tv = 0 if vc is None else vc.shape[-2]
+        L = 0 if vfull is None else vfull.shape[-2]
+        if tk + r != seen or tv + L != seen:
+            raise ValueError(f"inconsistent KIVI cache tuple: tk {tk} + r {r}, tv {tv} + L {L}, kv_seq_len {seen}")
+        if seen > self.max_tokens:
+            raise ValueError(f"cache tuple of {seen} tokens exceeds the capacity {self.max_tokens}")
+
+        def prep(t, shape, dtype):
+            if t is None:
+                return None
+            _lib.require_cuda(t)
+            assert tuple(t.shape) == shape and t.dtype == dtype, (tuple(t.shape), shape, t.dtype)
+            return t.contiguous()
+        kc = prep(kc, (B, Hkv, D, tk // kf), torch.int32)
+        ks, km = prep(ks, (B, Hkv, D, tk // g), torch.float16), prep(km, (B, Hkv, D, tk // g), torch.float16)
+        kfull = prep(kfull, (B, Hkv, r, D), torch.float16)
+        vc = prep(vc, (B, Hkv, tv, D // vf), torch.int32)
+        vs, vm = prep(vs, (B, Hkv, tv, D // g), torch.float16), prep(vm, (B, Hkv, tv, D // g), torch.float16)
+        vfull = prep(vfull, (B, Hkv, L, D), torch.float16)
+        ptr = lambda t: None if t is None or t.numel() == 0 else t.data_ptr()   # noqa: E731
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().kivi_cache_import_f16(
+                ctypes.byref(self._structs[layer]), tk, r, tv, L, ptr(kc), ptr(ks), ptr(km), ptr(kfull),
+                ptr(vc), ptr(vs), ptr(vm), ptr(vfull), _lib.stream_ptr(self.device)), "kivi_cache_import_f16")
+        self.tk, self.r, self.tv, self.L, self.vhead, self.kv_len = tk, r, tv, L, 0, seen
 
     def export(self, layer: int):
         """The reference's per-layer 9-tuple (models/llama_kivi.py:454-455):

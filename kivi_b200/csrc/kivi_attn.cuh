@@ -112,6 +112,7 @@ struct AttnParams {
     long long dbg_stride;
     Workspace w;
     int stage_bytes, spw /*stages per warp*/, hchunks, n_units, nw_eff /*warps that own an sv range*/;
+    int max_kv_len;                     // what the workspace rows were sized for
 };
 
 struct Sched {                          // per-step constants, identical for every unit
@@ -134,6 +135,14 @@ __device__ __forceinline__ Sched make_sched(const CacheDesc& c) {
     s.ipu = s.n_kb + s.n_kr + 1;
     s.bpu = s.n_vb + s.n_vr + 1;
     return s;
+}
+
+// The device-side lengths are trusted by every address computation below; a C-ABI caller that stepped past the sizes it
+// declared (max_kv_len, window capacities) must not corrupt memory: the kernels return without touching anything and
+// leave KIVI_STATE_ERR_CAPACITY in state[6] (surfaced by kivi_cache_read_state).
+__device__ __forceinline__ bool sched_ok(const Sched& s, const CacheDesc& c, int max_kv_len) {
+    return s.tk >= 0 && s.tv >= 0 && s.r >= 0 && s.L >= 0 && s.r < c.R && s.L <= c.R && s.T <= max_kv_len &&
+           s.tv + 1 <= max_kv_len && s.vhead >= 0 && s.vhead < c.v_res_cap && s.tk % c.R == 0;
 }
 
 struct Pipe {                           // a warp's private stages
@@ -618,6 +627,7 @@ qk_kernel(const AttnParams p)
     const Sched s = make_sched(c);
     const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
+    if (!sched_ok(s, c, p.max_kv_len)) { if (gw == 0 && lane == 0) c.state[6] = KIVI_STATE_ERR_CAPACITY; return; }
     KIVI_TL(0, gw, 0);
     const long long N = (long long)p.n_units * s.ipu;                        // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);
@@ -902,6 +912,7 @@ sv_kernel(const AttnParams p)
     const Sched s = make_sched(c);
     const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
+    if (!sched_ok(s, c, p.max_kv_len)) return;                               // the q.K^T kernel has flagged state[6]
     KIVI_TL(1, gw, 0);
     const long long N = (long long)p.n_units * s.bpu;                       // pseudo-blocks of the whole job
     const long long W = min((long long)p.nw_eff, N);                        // range owners: every range is non-empty
@@ -1193,27 +1204,18 @@ sv_kernel(const AttnParams p)
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 0, g_max_smem = 0;
-
-static inline void query_device() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
-}
-
 constexpr int kMaxCtasPerSm = kCW >= 16 ? 1 : 2;
 
-// workspace carve-up (shared by kivi_decode_workspace_bytes and the launcher)
+// workspace carve-up (shared by kivi_decode_workspace_bytes and the launcher); negative = KIVI_ERR_* / -cudaError
 static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, int max_kv_len, void* base, Workspace* w)
 {
-    query_device();
+    DeviceInfo di;
+    const int drc = device_info(&di);
+    if (drc) return drc < 0 ? drc : -(int64_t)drc;
     const int64_t rows = (int64_t)c.B * c.H;
     const int64_t ld = ((int64_t)max_kv_len + 16 + 127) / 128 * 128 + 128;
     const int bpu_max = cdiv(max_kv_len, kBlockTokens) + cdiv(c.R + 1, kResTile) + 4;
-    const int warps = g_num_sms * kMaxCtasPerSm * kCW;
+    const int warps = di.num_sms * kMaxCtasPerSm * kCW;
     const int part_cap = min(bpu_max, cdiv(warps, n_units) + 2);
     int64_t off = 0;
     auto take = [&](int64_t bytes) { const int64_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -1236,7 +1238,11 @@ template <int KB, int VB, int G, int GS>
 static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t st)
 {
     const CacheDesc& c = p.c;
-    query_device();
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const Tuning& tn = tuning();
+    const int max_smem = di.max_smem_optin;
     const int half_k = kHalfChunks * Lay<KB>::kChunkBytes + lay_meta_bytes(c.g) / kParts;
     const int half_v = kHalfChunks * Lay<VB>::kChunkBytes + lay_meta_bytes(c.g) / kParts + G * kPartTokens * 2;
     const int stage = max(max(half_k, half_v), kResBytes);
@@ -1245,27 +1251,23 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     int ctas = kMaxCtasPerSm;                                                // the kernels' __launch_bounds__
     p.spw = 0;
     for (; ctas >= 1; --ctas) {                                              // most CTAs per SM that still get >= 2 stages per warp
-        p.spw = min(4, (g_max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
+        p.spw = min(4, (max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
         if (p.spw >= 2) break;
     }
-    if (ctas < 1) { ctas = 1; p.spw = (g_max_smem - fixed) / (kCW * p.stage_bytes); }
-    if (const char* e = getenv("KIVI_CTAS_PER_SM")) {                        // tuning knobs (tools/microbench.py)
-        const int v = atoi(e);
-        if (v >= 1 && v <= ctas) { ctas = v; p.spw = min(8, (g_max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes)); }
+    if (ctas < 1) { ctas = 1; p.spw = (max_smem - fixed) / (kCW * p.stage_bytes); }
+    if (tn.ctas_per_sm >= 1 && tn.ctas_per_sm <= ctas) {                     // tuning knobs (tools/microbench.py), read once per process
+        ctas = tn.ctas_per_sm;
+        p.spw = min(8, (max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
     }
-    if (const char* e = getenv("KIVI_STAGES_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= p.spw) p.spw = v; }
+    if (tn.stages_per_warp >= 1 && tn.stages_per_warp <= p.spw) p.spw = tn.stages_per_warp;
     if (p.spw < 1) return KIVI_ERR_CAPACITY;
     const size_t smem = (size_t)kCW * p.spw * p.stage_bytes + fixed;
     auto kqk = qk_kernel<KB, G, GS>;
     auto ksv = sv_kernel<KB, VB, G, GS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kqk, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ksv, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    const int grid = g_num_sms * ctas;
+    static std::atomic<unsigned long long> optin_qk{0}, optin_sv{0};        // per kernel instantiation, one bit per device
+    rc = ensure_dynamic_smem(kqk, max_smem, di.ordinal, optin_qk); if (rc) return rc;
+    rc = ensure_dynamic_smem(ksv, max_smem, di.ordinal, optin_sv); if (rc) return rc;
+    const int grid = di.num_sms * ctas;
     // range owners: at least one pseudo-block each (the kernels clamp to the number of pseudo-blocks), and never more
     // ranges per unit than the workspace has record / statistics slots: part_cap - 2 warps per unit at most
     const long long want = (long long)p.n_units * max(1, p.w.part_cap - 2);
@@ -1273,7 +1275,7 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     // programmatic dependent launch: the p.V prologue (setup, cache lengths) overlaps the q.K^T tail; the q.K^T prologue
     // (setup, lengths, first K blocks in flight) overlaps the tail of the previous kernel of the stream only when the
     // caller has promised that that kernel does not write the cache (KIVI_CACHE_OVERLAP_PROLOGUE)
-    const bool pdl = getenv("KIVI_NO_PDL") == nullptr;
+    const bool pdl = !tn.no_pdl;
     cudaLaunchAttribute attr_qk[1], attr_sv[1];
     attr_qk[0].id = attr_sv[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr_qk[0].val.programmaticStreamSerializationAllowed = pdl && overlap_prologue ? 1 : 0;
@@ -1283,7 +1285,7 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     cfg.attrs = attr_qk; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kqk, p);
     if (e != cudaSuccess) return (int)e;
-    int rc = post_launch(); if (rc) return rc;
+    rc = post_launch(); if (rc) return rc;
     cfg.attrs = attr_sv;
     e = cudaLaunchKernelEx(&cfg, ksv, p);
     if (e != cudaSuccess) return (int)e;

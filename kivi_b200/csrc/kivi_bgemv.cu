@@ -41,7 +41,7 @@ template <int BITS>
 __device__ __forceinline__ float cell_rescale(int e) { return field_rescale<BITS>(e % (32 / BITS)); }
 
 // ------------------------------------------------------------------------------------------------
-// wide: one warp = 1024 consecutive n, loops over all K rows.  grid = (n-tiles/4, U_kv, ratio/G)
+// wide: one warp = 1024 consecutive n, loops over all K rows.  grid = (U_kv, n-tiles/4, ratio/G)
 // ------------------------------------------------------------------------------------------------
 constexpr int kWideKTile = 128;
 
@@ -57,9 +57,9 @@ bgemv_ref_wide_kernel(const __half* __restrict__ A, int64_t a_stride,
     __shared__ float xs[G][kWideKTile];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ukv = blockIdx.y;
+    const int ukv = blockIdx.x;
     const int h0 = blockIdx.z * G;                               // first query head of this chunk
-    const int cell = (blockIdx.x * 4 + warp) * 32 + lane;
+    const int cell = (blockIdx.y * 4 + warp) * 32 + lane;
     const int n0 = cell * 32;
     const bool valid = n0 < N;
 
@@ -124,7 +124,7 @@ bgemv_ref_wide_kernel(const __half* __restrict__ A, int64_t a_stride,
 
 // ------------------------------------------------------------------------------------------------
 // tall: N <= 256.  lanes = (row class rc, cell ng); 8 warps split the rows.
-// grid = (1, U_kv, ratio/G), block = 256
+// grid = (U_kv, 1, ratio/G), block = 256
 // ------------------------------------------------------------------------------------------------
 template <int BITS, int G>
 __global__ void __launch_bounds__(256)
@@ -141,7 +141,7 @@ bgemv_ref_tall_kernel(const __half* __restrict__ A, int64_t a_stride,
     const int ngp = 1 << ng_log2;
     const int ng = lane & (ngp - 1), rc = lane >> ng_log2;
     const int rpw = 32 >> ng_log2;                               // rows per warp step
-    const int ukv = blockIdx.y;
+    const int ukv = blockIdx.x;
     const int h0 = blockIdx.z * G;
     const int n0 = ng * 32;
     const bool cell_ok = n0 < N;
@@ -221,8 +221,8 @@ bgemv_ref_generic_kernel(const __half* __restrict__ A, int64_t a_stride,
                          __half* __restrict__ C, int ratio, int K, int N, int g)
 {
     constexpr int FPI = 32 / BITS;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int uq = blockIdx.y;
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    const int uq = blockIdx.x;
     if (n >= N) return;
     const int ukv = uq / ratio;
     const uint32_t* wp = qB + ukv * qb_us + n / FPI;
@@ -253,8 +253,8 @@ bgemv_kernel_layout_kernel(const __half* __restrict__ A, int64_t a_stride,
 {
     constexpr int FPI = 32 / BITS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * 4 + warp;                         // packed row
-    const int uq = blockIdx.y;
+    const int p = blockIdx.y * 4 + warp;                         // packed row
+    const int uq = blockIdx.x;
     if (p >= OC / FPI) return;
     const int ukv = uq / ratio;
     const int grp = (p * FPI) / g;
@@ -313,8 +313,8 @@ gemv_inner_kernel(const __half* __restrict__ in, const uint32_t* __restrict__ ke
 {
     constexpr int FPI = 32 / BITS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int oc = blockIdx.x * 4 + warp;
-    const int b = blockIdx.y;
+    const int oc = blockIdx.y * 4 + warp;
+    const int b = blockIdx.x;
     if (oc >= OC) return;
     const int nw = IC / FPI;
     float acc = 0.f;
@@ -351,7 +351,7 @@ static int launch_ref_fast(const GemvArgs& a) {
     const int ratio = a.nh / a.nh_kv;
     const int ukv = a.B * a.nh_kv;
     if (a.N > 256) {
-        dim3 grid(cdiv(cdiv(a.N, 1024), 4), ukv, ratio / G);
+        dim3 grid(ukv, cdiv(cdiv(a.N, 1024), 4), ratio / G);
         bgemv_ref_wide_kernel<BITS, G><<<grid, 128, 0, a.st>>>(a.A, a.a_stride, a.qB, a.qb_us, a.qb_rs, a.S, a.Z,
                                                                a.sz_us, a.sz_rs, a.C, ratio, a.K, a.N, a.g);
     } else {
@@ -360,7 +360,7 @@ static int launch_ref_fast(const GemvArgs& a) {
         const size_t smem = (size_t)8 * (1 << lg) * G * 33 * sizeof(float);
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(bgemv_ref_tall_kernel<BITS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid(1, ukv, ratio / G);
+        dim3 grid(ukv, 1, ratio / G);
         bgemv_ref_tall_kernel<BITS, G><<<grid, 256, smem, a.st>>>(a.A, a.a_stride, a.qB, a.qb_us, a.qb_rs, a.S, a.Z,
                                                                   a.sz_us, a.sz_rs, a.C, ratio, a.K, a.N, a.g, lg);
     }
@@ -373,7 +373,7 @@ static int launch_bgemv(const GemvArgs& a, int layout) {
     const int ratio = a.nh / a.nh_kv;
     const int uq = a.B * a.nh;
     if (layout == KIVI_LAYOUT_KERNEL) {
-        dim3 grid(cdiv(a.N / FPI, 4), uq);
+        dim3 grid(uq, cdiv(a.N / FPI, 4));
         bgemv_kernel_layout_kernel<BITS><<<grid, 128, 0, a.st>>>(a.A, a.a_stride, a.qB, a.qb_us, a.qb_rs, a.S, a.Z,
                                                                   a.sz_us, a.sz_rs, a.C, ratio, a.K, a.N, a.g);
         return post_launch();
@@ -388,7 +388,7 @@ static int launch_bgemv(const GemvArgs& a, int layout) {
         if (ratio % 2 == 0) return launch_ref_fast<BITS, 2>(a);
         return launch_ref_fast<BITS, 1>(a);
     }
-    dim3 grid(cdiv(a.N, 128), uq);
+    dim3 grid(uq, cdiv(a.N, 128));
     bgemv_ref_generic_kernel<BITS><<<grid, 128, 0, a.st>>>(a.A, a.a_stride, a.qB, a.qb_us, a.qb_rs, a.S, a.Z,
                                                             a.sz_us, a.sz_rs, a.C, ratio, a.K, a.N, a.g);
     return post_launch();
@@ -412,12 +412,12 @@ extern "C" int kivi_bgemv_outer_f16(const void* A, int64_t a_stride,
     if (N % group_size != 0) return KIVI_ERR_SHAPE;
     if (B == 0 || N == 0) return KIVI_OK;
     if (!A || !qB || !scales || !zeros || !C) return KIVI_ERR_NULL;
-    if ((int64_t)B * nh > 65535) return KIVI_ERR_SHAPE;
+    if ((int64_t)B * nh > 0x7fffffff || (int64_t)N / 128 > 65535 * 4) return KIVI_ERR_UNSUPPORTED;   // grid.x = units, grid.y = column tiles
     kivi::GemvArgs a{(const __half*)A, a_stride, (const uint32_t*)qB, qb_unit_stride, qb_row_stride,
                      (const __half*)scales, (const __half*)zeros, sz_unit_stride, sz_row_stride,
                      (__half*)C, B, nh, nh_kv, K, N, group_size, (cudaStream_t)stream};
     if (bits == 8) {   // Triton-surface only (quant/matmul.py:112-175 accepts 8-bit): slow exact path
-        dim3 grid(kivi::cdiv(N, 128), B * nh);
+        dim3 grid(B * nh, kivi::cdiv(N, 128));
         kivi::bgemv_ref_generic_kernel<8><<<grid, 128, 0, a.st>>>(a.A, a.a_stride, a.qB, a.qb_us, a.qb_rs, a.S, a.Z,
                                                                a.sz_us, a.sz_rs, a.C, nh / nh_kv, K, N, group_size);
         return kivi::post_launch();
@@ -436,8 +436,7 @@ extern "C" int kivi_gemv_inner_f16(const void* in, const void* kernel, const voi
     if (sf_w < kivi::cdiv(IC, group_size)) return KIVI_ERR_SHAPE;
     if (Bn == 0 || OC == 0) return KIVI_OK;
     if (!in || !kernel || !scales || !zeros || !out) return KIVI_ERR_NULL;
-    if (Bn > 65535) return KIVI_ERR_SHAPE;
-    dim3 grid(kivi::cdiv(OC, 4), Bn);
+    dim3 grid(Bn, kivi::cdiv(OC, 4));
     cudaStream_t st = (cudaStream_t)stream;
     #define KIVI_INNER(BITS_) kivi::gemv_inner_kernel<BITS_><<<grid, 128, 0, st>>>( \
         (const __half*)in, (const uint32_t*)kernel, (const __half*)scales, (const __half*)zeros, (__half*)out, \

@@ -183,6 +183,76 @@ export_kv_kernel(CacheDesc c, int tk, int tv, int L, int vhead, int r,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// import from the reference layouts: the inverse of export_kv_kernel.  One thread per destination word / meta half / window
+// element; every byte of the blocks that hold imported tokens is written (codes of tokens past the end are zero).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+import_kv_kernel(CacheDesc c, int tk, int tv, int L, int r,
+                 const uint32_t* __restrict__ k_code, const __half* __restrict__ k_scale, const __half* __restrict__ k_mn,
+                 const uint32_t* __restrict__ v_code, const __half* __restrict__ v_scale, const __half* __restrict__ v_mn,
+                 const __half* __restrict__ k_full, const __half* __restrict__ v_full)
+{
+    const int u = blockIdx.y, g = c.g, ngrp = 128 / g;
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int isv = 0; isv < 2; ++isv) {                    // 0: K store (inner = channel, outer = token), 1: V store
+        const int bits = isv ? c.v_bits : c.k_bits, fpi = 32 / bits, n_tok = isv ? tv : tk;
+        const int F = 16 / bits, slab_rows = 16 * F, slabs = 128 / slab_rows, wpb = 8 * slabs * 128;   // words per block
+        const int bb = lay_block_bytes(bits, g), nblk = cdiv(n_tok, kBlockTokens);
+        uint8_t* ub = (isv ? c.v_store : c.k_store) + (int64_t)u * (isv ? c.v_cap_blocks : c.k_cap_blocks) * bb;
+        const uint32_t* code = isv ? v_code : k_code;
+        const __half* sc = isv ? v_scale : k_scale;
+        const __half* mn = isv ? v_mn : k_mn;
+        const int wpr_k = tk / fpi, gpr_k = tk / g;        // K: words / groups per channel row
+        const int wpt_v = kD / fpi, gpt_v = kD / g;        // V: words / groups per token row
+        for (int i = tid; i < nblk * wpb; i += stride) {
+            const int blk = i / wpb, w = i % wpb;
+            const int ch = w / (slabs * 128), sl = (w / 128) % slabs, lw = w % 128;
+            const int lane = lw >> 2, rr = lw & 3;
+            const int row = (lane >> 2) + 8 * (rr & 1);
+            const int i0 = ch * 16 + 2 * (lane & 3) + 8 * (rr >> 1);
+            uint32_t word = 0;
+            for (int par = 0; par < 2; ++par) {
+                const int inner = i0 + par;
+                for (int j = 0; j < F; ++j) {
+                    const int o = sl * slab_rows + 16 * j + row;
+                    uint32_t cd = 0;
+                    if (!isv) {
+                        const int tok = blk * kBlockTokens + o;
+                        if (tok < tk) cd = (code[((int64_t)u * kD + inner) * wpr_k + tok / fpi] >> (bits * (tok % fpi))) & ((1u << bits) - 1u);
+                    } else {
+                        const int tok = blk * kBlockTokens + inner;
+                        if (tok < tv) cd = (code[((int64_t)u * tv + tok) * wpt_v + o / fpi] >> (bits * (o % fpi))) & ((1u << bits) - 1u);
+                    }
+                    word |= cd << (16 * par + bits * j);
+                }
+            }
+            reinterpret_cast<uint32_t*>(ub + (int64_t)blk * bb)[w] = word;
+        }
+        for (int i = tid; i < nblk * 128 * ngrp; i += stride) {
+            const int blk = i / (128 * ngrp), inner = (i / ngrp) % 128, G = i % ngrp;
+            __half s = __float2half_rn(0.f), z = s;
+            if (!isv) {
+                const int tok = blk * kBlockTokens + G * g;
+                if (tok < tk) { s = sc[((int64_t)u * kD + inner) * gpr_k + tok / g]; z = mn[((int64_t)u * kD + inner) * gpr_k + tok / g]; }
+            } else {
+                const int tok = blk * kBlockTokens + inner;
+                if (tok < tv) { s = sc[((int64_t)u * tv + tok) * gpt_v + G]; z = mn[((int64_t)u * tv + tok) * gpt_v + G]; }
+            }
+            *reinterpret_cast<__half*>(ub + (int64_t)blk * bb + lay_scale_off(bits, g, inner, G)) = s;
+            *reinterpret_cast<__half*>(ub + (int64_t)blk * bb + lay_zero_off(bits, g, inner, G)) = z;
+        }
+    }
+    for (int i = tid; i < r * kD; i += stride)
+        c.k_res[(int64_t)u * c.R * kD + win_off(i / kD, i % kD)] = k_full[(int64_t)u * r * kD + i];
+    for (int i = tid; i < L * kD; i += stride)
+        c.v_res[(int64_t)u * c.v_res_cap * kD + win_off(i / kD, i % kD)] = v_full[(int64_t)u * L * kD + i];
+    if (u == 0 && tid == 0) {
+        c.state[ST_TK] = tk; c.state[ST_R] = r; c.state[ST_TV] = tv; c.state[ST_L] = L;
+        c.state[ST_VHEAD] = 0; c.state[ST_KVLEN] = tk + r; c.state[6] = 0; c.state[7] = 0;
+    }
+}
+
 int make_desc(const kivi_cache_t* k, CacheDesc* d)
 {
     if (!k) return KIVI_ERR_NULL;
@@ -244,16 +314,16 @@ extern "C" int kivi_cache_prefill_f16(const kivi_cache_t* cache, const void* k, 
     if (cdiv(nqk, kBlockTokens) > c.k_cap_blocks || cdiv(nqv, kBlockTokens) > c.v_cap_blocks) return KIVI_ERR_CAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
     const int U = c.B * c.Hkv;
-    if (U > 65535) return KIVI_ERR_SHAPE;
+    if (U > 65535) return KIVI_ERR_UNSUPPORTED;                     // grid.y
     const size_t smem = (size_t)kBlockTokens * (kD + 8) * 2 + (size_t)kD * (kD + 4);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(block_prefill_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(block_prefill_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(block_prefill_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(block_prefill_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
+    DeviceInfo di;
+    rc = device_info(&di);
+    if (rc) return rc;
+    static std::atomic<unsigned long long> optin[4];                 // 51.7 KB of dynamic shared memory: opt-in per device
+    rc = ensure_dynamic_smem(block_prefill_kernel<2, true>, (int)smem, di.ordinal, optin[0]); if (rc) return rc;
+    rc = ensure_dynamic_smem(block_prefill_kernel<4, true>, (int)smem, di.ordinal, optin[1]); if (rc) return rc;
+    rc = ensure_dynamic_smem(block_prefill_kernel<2, false>, (int)smem, di.ordinal, optin[2]); if (rc) return rc;
+    rc = ensure_dynamic_smem(block_prefill_kernel<4, false>, (int)smem, di.ordinal, optin[3]); if (rc) return rc;
     if (nqk > 0) {
         dim3 grid(cdiv(nqk, kBlockTokens), U);
         if (c.k_bits == 2) block_prefill_kernel<2, true><<<grid, 256, smem, st>>>(c, (const __half*)k, n, nqk);
@@ -293,4 +363,36 @@ extern "C" int kivi_cache_export_f16(const kivi_cache_t* cache, int tk, int r, i
         (uint32_t*)k_code, (__half*)k_scale, (__half*)k_mn, (uint32_t*)v_code, (__half*)v_scale, (__half*)v_mn,
         (__half*)k_full, (__half*)v_full);
     return post_launch();
+}
+
+extern "C" int kivi_cache_import_f16(const kivi_cache_t* cache, int tk, int r, int tv, int L,
+                                     const void* k_code, const void* k_scale, const void* k_mn, const void* k_full,
+                                     const void* v_code, const void* v_scale, const void* v_mn, const void* v_full, void* stream)
+{
+    CacheDesc c;
+    int rc = make_desc(cache, &c);
+    if (rc) return rc;
+    if (tk < 0 || r < 0 || tv < 0 || L < 0 || tk % c.R != 0 || r >= c.R || L > c.R || tk + r != tv + L) return KIVI_ERR_SHAPE;
+    if (tv > 0 && L != c.R) return KIVI_ERR_SHAPE;                  // the V store fills only once the window is full (:442-452)
+    if (cdiv(tk, kBlockTokens) > c.k_cap_blocks || cdiv(tv, kBlockTokens) > c.v_cap_blocks) return KIVI_ERR_CAPACITY;
+    if (tk > 0 && (!k_code || !k_scale || !k_mn)) return KIVI_ERR_NULL;
+    if (tv > 0 && (!v_code || !v_scale || !v_mn)) return KIVI_ERR_NULL;
+    if ((r > 0 && !k_full) || (L > 0 && !v_full)) return KIVI_ERR_NULL;
+    const int U = c.B * c.Hkv;
+    if (U > 65535) return KIVI_ERR_UNSUPPORTED;
+    import_kv_kernel<<<dim3(8, U), 256, 0, (cudaStream_t)stream>>>(c, tk, tv, L, r,
+        (const uint32_t*)k_code, (const __half*)k_scale, (const __half*)k_mn,
+        (const uint32_t*)v_code, (const __half*)v_scale, (const __half*)v_mn, (const __half*)k_full, (const __half*)v_full);
+    return post_launch();
+}
+
+extern "C" int kivi_cache_read_state(const kivi_cache_t* cache, int32_t* host_state8, void* stream)
+{
+    CacheDesc c;
+    int rc = make_desc(cache, &c);
+    if (rc) return rc;
+    if (!host_state8) return KIVI_ERR_NULL;
+    cudaError_t e = cudaMemcpyAsync(host_state8, c.state, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? KIVI_OK : (int)e;
 }

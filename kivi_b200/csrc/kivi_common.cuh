@@ -13,15 +13,40 @@
 #error "libkivi_b200 is written for sm_100a (B200) only"
 #endif
 
+#include <atomic>
+
 namespace kivi {
 
-extern unsigned long long g_launch_count;   // host-side counter (kivi_api.cu)
+extern std::atomic<unsigned long long> g_launch_count;   // host-side counter (kivi_api.cu)
 
 inline int post_launch() {
-    ++g_launch_count;
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIVI_OK : (int)e;
 }
+
+// Properties of the CURRENT device of the calling thread, cached per device ordinal (kivi_api.cu): a process may drive
+// several GPUs (device_map="auto" in the reference), and every limit / opt-in below is per device.
+constexpr int kMaxDevices = 64;
+struct DeviceInfo { int ordinal, num_sms, max_smem_optin; };
+int device_info(DeviceInfo* out);            // 0 or a cudaError_t
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device only: `done` is a per-kernel bit mask
+// of the device ordinals that already have the opt-in (one static mask per kernel instantiation at the call site).
+template <class F>
+inline int ensure_dynamic_smem(F kernel, int bytes, int ordinal, std::atomic<unsigned long long>& done) {
+    const unsigned long long bit = 1ull << (ordinal & 63);
+    if (done.load(std::memory_order_acquire) & bit) return KIVI_OK;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    done.fetch_or(bit, std::memory_order_release);
+    return KIVI_OK;
+}
+
+// Tuning knobs from the environment, read ONCE per process (kivi_api.cu); 0 = not set.  Production callers never set
+// them (tools/microbench.py, tools/sweep_*.sh do).
+struct Tuning { int gqa_g, ctas_per_sm, stages_per_warp, no_pdl; };
+const Tuning& tuning();
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

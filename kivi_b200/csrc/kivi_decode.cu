@@ -12,9 +12,12 @@ int attention_k4v2(AttnParams& p, int G, bool overlap_prologue, cudaStream_t st)
 
 using namespace kivi;
 
-static int gqa_chunk(int ratio) {
+// query heads of a KV head that share one unit's MMAs: from the cache geometry, or the explicit KIVI_CACHE_GQA_CHUNK
+// field of cache->flags (the same struct sizes the workspace and launches, so both always agree)
+static int gqa_chunk(int ratio, int flags) {
     int G = ratio % 4 == 0 ? 4 : (ratio % 2 == 0 ? 2 : 1);
-    if (const char* e = getenv("KIVI_GQA_G")) { const int g = atoi(e); if ((g == 1 || g == 2 || g == 4) && ratio % g == 0) G = g; }
+    const int want = (flags >> KIVI_CACHE_GQA_CHUNK_SHIFT) & 7;
+    if ((want == 1 || want == 2 || want == 4) && ratio % want == 0) G = want;
     return G;
 }
 
@@ -24,7 +27,7 @@ extern "C" int64_t kivi_decode_workspace_bytes(const kivi_cache_t* cache, int ma
     int rc = make_desc(cache, &c);
     if (rc) return rc;
     if (max_kv_len <= 0) return KIVI_ERR_SHAPE;
-    const int ratio = c.H / c.Hkv, G = gqa_chunk(ratio);
+    const int ratio = c.H / c.Hkv, G = gqa_chunk(ratio, cache->flags);
     return carve_workspace(c, c.B * c.Hkv * (ratio / G), G, max_kv_len, nullptr, nullptr);
 }
 
@@ -43,10 +46,13 @@ extern "C" int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* 
     p.out = (__half*)out; p.dbg_logits = (__half*)dbg_logits; p.dbg_probs = (__half*)dbg_probs; p.dbg_stride = dbg_stride;
     const bool overlap = (cache->flags & KIVI_CACHE_OVERLAP_PROLOGUE) != 0;   // the q.K^T launch may overlap its predecessor
     const int ratio = p.c.H / p.c.Hkv;
-    const int G = gqa_chunk(ratio);
+    const int G = gqa_chunk(ratio, cache->flags);
     p.hchunks = ratio / G;
     p.n_units = p.c.B * p.c.Hkv * p.hchunks;
-    if (carve_workspace(p.c, p.n_units, G, max_kv_len, workspace, &p.w) > workspace_bytes) return KIVI_ERR_CAPACITY;
+    p.max_kv_len = max_kv_len;
+    const int64_t need = carve_workspace(p.c, p.n_units, G, max_kv_len, workspace, &p.w);
+    if (need < 0) return (int)need;
+    if (need > workspace_bytes) return KIVI_ERR_CAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
     if (p.c.k_bits == 2 && p.c.v_bits == 2) return attention_k2v2(p, G, overlap, st);
     if (p.c.k_bits == 4 && p.c.v_bits == 4) return attention_k4v4(p, G, overlap, st);

@@ -70,7 +70,7 @@ add_rmsnorm_kernel(const __half* __restrict__ x, __half* __restrict__ residual, 
 __global__ void __launch_bounds__(64)
 rope_split_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos_t, const __half* __restrict__ sin_t,
                   const long long* __restrict__ pos, __half* __restrict__ q, __half* __restrict__ k, __half* __restrict__ v,
-                  int H, int Hkv)
+                  int H, int Hkv, int table_rows)
 {
     constexpr int D = 128;
     // the q.K^T kernel that follows is launched with programmatic serialization: let it set up and start streaming K blocks
@@ -83,7 +83,8 @@ rope_split_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos
         dst[i] = src[i]; dst[i + 64] = src[i + 64];
         return;
     }
-    const long long p = pos[b];
+    long long p = pos[b];
+    p = p < 0 ? 0 : (p >= table_rows ? table_rows - 1 : p);                  // never read outside the tables (the host checks the range)
     const __half c0 = cos_t[p * D + i], c1 = cos_t[p * D + i + 64];
     const __half s0 = sin_t[p * D + i], s1 = sin_t[p * D + i + 64];
     const __half x0 = src[i], x1 = src[i + 64];
@@ -124,13 +125,14 @@ extern "C" int kivi_add_rmsnorm_f16(const void* x, void* residual, const void* w
 }
 
 extern "C" int kivi_rope_split_f16(const void* qkv, const void* cos_table, const void* sin_table, const void* pos,
-                                   void* q, void* k, void* v, int batch, int num_heads, int num_kv_heads, void* stream)
+                                   void* q, void* k, void* v, int batch, int num_heads, int num_kv_heads, int table_rows,
+                                   void* stream)
 {
     if (!qkv || !cos_table || !sin_table || !pos || !q || !k || !v) return KIVI_ERR_NULL;
-    if (batch <= 0 || num_heads <= 0 || num_kv_heads <= 0 || batch > 65535) return KIVI_ERR_SHAPE;
+    if (batch <= 0 || num_heads <= 0 || num_kv_heads <= 0 || batch > 65535 || table_rows <= 0) return KIVI_ERR_SHAPE;
     rope_split_kernel<<<dim3(num_heads + 2 * num_kv_heads, batch), 64, 0, (cudaStream_t)stream>>>(
         (const __half*)qkv, (const __half*)cos_table, (const __half*)sin_table, (const long long*)pos,
-        (__half*)q, (__half*)k, (__half*)v, num_heads, num_kv_heads);
+        (__half*)q, (__half*)k, (__half*)v, num_heads, num_kv_heads, table_rows);
     return post_launch();
 }
 

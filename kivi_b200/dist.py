@@ -1,4 +1,4 @@
-"""Multi-GPU decode: data-parallel replicas over the batch, one all-gather of the logits per step.
+"""Multi-GPU decode: data-parallel replicas over the batch, one all-gather per step at the sampling point.
 
 Every (b, kv-head) unit of the KIVI hot path is independent, so the batch is sharded in
 contiguous ranges, each rank runs the whole model on its shard with NO per-layer collective, and the
@@ -68,6 +68,24 @@ def greedy_next_tokens(local_logits: torch.Tensor, rank: int, world_size: int, g
     toks = full.argmax(-1)
     lo, hi = shard_range(global_batch, rank, world_size)
     return toks, toks[lo:hi]
+
+
+def gather_tokens(local_tokens: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Greedy sampling needs no logits from the other shards: argmax is local to a sequence, so the exchange shrinks to
+    the sampled ids themselves, 8 bytes per sequence (`gather_logits` stays the general path, e.g. for samplers that
+    need the whole distribution on one rank).  local_tokens [B_local] int64 -> [B_global] (rank order = batch order,
+    equal shards).  `out` may be a preallocated [world_size * B_local] buffer: the call is then allocation-free and
+    capturable in a CUDA graph (NCCL all-gathers are)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        if out is not None:
+            out.copy_(local_tokens)
+            return out
+        return local_tokens
+    ws = dist.get_world_size()
+    if out is None:
+        out = torch.empty(ws * local_tokens.numel(), dtype=local_tokens.dtype, device=local_tokens.device)
+    dist.all_gather_into_tensor(out, local_tokens.contiguous().view(-1))
+    return out
 
 
 def barrier():

@@ -17,7 +17,7 @@ def _bind():
         return
     vp, i32 = ctypes.c_void_p, ctypes.c_int
     _lib.bind("kivi_add_rmsnorm_f16", i32, [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp])
-    _lib.bind("kivi_rope_split_f16", i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp])
+    _lib.bind("kivi_rope_split_f16", i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp])
     _lib.bind("kivi_silu_mul_f16", i32, [vp, vp, i32, i32, vp])
     _B = True
 
@@ -37,7 +37,7 @@ def rope_split(qkv, cos_table, sin_table, pos, q, k, v):
     _bind()
     B, H, Hkv = q.shape[0], q.shape[1], k.shape[1]
     _lib.check(_lib.lib().kivi_rope_split_f16(qkv.data_ptr(), cos_table.data_ptr(), sin_table.data_ptr(), pos.data_ptr(),
-                                              q.data_ptr(), k.data_ptr(), v.data_ptr(), B, H, Hkv,
+                                              q.data_ptr(), k.data_ptr(), v.data_ptr(), B, H, Hkv, cos_table.shape[0],
                                               _lib.stream_ptr(qkv.device)), "kivi_rope_split_f16")
 
 

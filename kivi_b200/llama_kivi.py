@@ -190,18 +190,26 @@ class LlamaFlashAttention_KIVI(nn.Module):
         k = k * cos + _rotate_half(k) * sin
         return q, k, v
 
+    def _prompt_attention(self, q, k, v, attention_mask):
+        """Attention over the prompt itself (the reference calls flash-attn here, models/llama_kivi.py:401-423; off the
+        decode hot path): causal, plus the additive mask [B, 1, q_len, q_len] when the batch is padded."""
+        kk, vv = repeat_kv(k, self.num_key_value_groups), repeat_kv(v, self.num_key_value_groups)
+        if attention_mask is None:
+            return F.scaled_dot_product_attention(q, kk, vv, is_causal=True)
+        return F.scaled_dot_product_attention(q, kk, vv, attn_mask=attention_mask.to(q.dtype))
+
     def forward(self, hidden_states, cos, sin, past_key_value=None, attention_mask=None):
         """hidden_states [B, q_len, hidden]; cos/sin broadcastable to [B, 1, q_len, D].
         past_key_value: None (prefill, returns a 9-tuple), a 9-tuple (reference semantics), or a
-        (KiviCache, layer) pair (fused path; prefill fills it, decode is one launch)."""
+        (KiviCache, layer) pair (fused path; prefill fills it, decode is one launch).
+        attention_mask: None or additive [B, 1, q_len, kv_len] (models/llama_kivi.py:364-372)."""
         bsz, q_len, _ = hidden_states.shape
         q, k, v = self._qkv(hidden_states, cos, sin)
         fused = isinstance(past_key_value, tuple) and len(past_key_value) == 2 and isinstance(past_key_value[0], KiviCache)
         if fused:
             cache, layer = past_key_value
             if q_len > 1:                                                   # prefill (:401-452)
-                attn_output = F.scaled_dot_product_attention(q, repeat_kv(k, self.num_key_value_groups),
-                                                             repeat_kv(v, self.num_key_value_groups), is_causal=True)
+                attn_output = self._prompt_attention(q, k, v, attention_mask)
                 cache.prefill(layer, k, v)
                 attn_output = attn_output.transpose(1, 2).reshape(bsz, q_len, self.hidden_size)
             else:                                                           # decode (:314-399), one launch
@@ -216,9 +224,7 @@ class LlamaFlashAttention_KIVI(nn.Module):
                                                             self.v_bits, self.residual_length, attention_mask)
             attn_output = attn_output.transpose(1, 2).contiguous()
         else:                                                               # prefill -> 9-tuple
-            attn_output = F.scaled_dot_product_attention(q, repeat_kv(k, self.num_key_value_groups),
-                                                         repeat_kv(v, self.num_key_value_groups), is_causal=True)
-            attn_output = attn_output.transpose(1, 2)
+            attn_output = self._prompt_attention(q, k, v, attention_mask).transpose(1, 2)
             past = kivi_prefill_tuple(k, v, self.group_size, self.k_bits, self.v_bits, self.residual_length)
         attn_output = attn_output.reshape(bsz, q_len, self.hidden_size)
         return self.o_proj(attn_output), None, past
@@ -262,24 +268,115 @@ class LlamaModel_KIVI(nn.Module):
         self.norm = LlamaRMSNorm(config.hidden_size, config.rms_norm_eps)
 
 
+class _Output(tuple):
+    """What forward() returns when no transformers ModelOutput class is wanted: a (logits, past_key_values) tuple that
+    also answers to the attribute names of CausalLMOutputWithPast."""
+    __slots__ = ()
+    loss = None
+    logits = property(lambda self: self[0])
+    past_key_values = property(lambda self: self[1])
+
+
+def _additive_mask(attention_mask, q_len: int, total: int, dtype, device):
+    """HF padding mask [B, total] (1 = attend) -> additive [B, 1, q_len, total] with the causal structure, or None
+    when nothing is masked; a 4-D additive mask passes through (what the reference's hook receives, :364-372)."""
+    if attention_mask is None:
+        return None
+    if attention_mask.dim() == 4:
+        return attention_mask
+    keep = attention_mask[:, None, None, :total].to(torch.bool)
+    if q_len == 1 and bool(keep.all()):
+        return None
+    if q_len > 1:
+        causal = torch.ones((q_len, total), dtype=torch.bool, device=device).tril(total - q_len)
+        keep = keep & causal
+    else:
+        keep = keep.expand(-1, 1, 1, total)
+    return torch.zeros(keep.shape, dtype=dtype, device=device).masked_fill(~keep, torch.finfo(dtype).min)
+
+
 class LlamaForCausalLM_KIVI(nn.Module):
-    """models/llama_kivi.py:785.  `decode_step` / `generate` use the fused cache path; `forward` keeps the
-    reference's (logits, past_key_values) contract with the legacy per-layer 9-tuples."""
+    """models/llama_kivi.py:785.  `forward` keeps the reference's contract (HF argument names, per-layer 9-tuples as
+    past_key_values, fp32 logits, `prepare_inputs_for_generation`, `_reorder_cache`); `decode_step` / `generate` use
+    the fused cache path (pre-allocated KiviCache, the step captured in a CUDA graph)."""
 
     def __init__(self, config):
         super().__init__()
         self.config = config
+        self.vocab_size = config.vocab_size
         self.model = LlamaModel_KIVI(config)
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
         self._rope = None
         self.cache: KiviCache | None = None
         self._graph = None
+        self._fast = None
+        self._dist_tokens = None            # [world * B] ids gathered inside the step (greedy sampling, world > 1)
+        self._dist_in_graph = True
+
+    # ------------------------------------------------------------------ HF-style construction
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, config=None, torch_dtype=torch.float16, device_map=None,
+                        **unused):
+        """Load a LOCAL Hugging Face Llama / Mistral checkpoint directory (config.json + *.safetensors or
+        pytorch_model*.bin; there is no network here) into the KIVI model, as the reference's
+        LlamaForCausalLM_KIVI.from_pretrained(config=...) does (example.py:22-28, mem_spd_test.py:24-31).  `config` is
+        the user's config object carrying k_bits / v_bits / group_size / residual_length (models/llama_kivi.py:34-38);
+        without one, config.json is read and the KIVI attributes default to K2V2 g32 R128."""
+        import glob
+        import json
+        import os
+        path = str(pretrained_model_name_or_path)
+        if not os.path.isdir(path):
+            raise FileNotFoundError(f"{path}: from_pretrained needs a local checkpoint directory (no network on this box)")
+        if config is None:
+            with open(os.path.join(path, "config.json")) as f:
+                raw = json.load(f)
+            config = SimpleNamespace(**raw)
+        for name, dflt in (("k_bits", 2), ("v_bits", 2), ("group_size", 32), ("residual_length", 128), ("use_flash", True)):
+            if not hasattr(config, name):
+                setattr(config, name, dflt)
+        model = cls(config)
+        state = {}
+        files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+        if files:
+            from safetensors.torch import load_file
+            for fn in files:
+                state.update(load_file(fn))
+        else:
+            for fn in sorted(glob.glob(os.path.join(path, "pytorch_model*.bin"))):
+                state.update(torch.load(fn, map_location="cpu", weights_only=True))
+        if not state:
+            raise FileNotFoundError(f"{path}: no *.safetensors / pytorch_model*.bin weights found")
+        if "lm_head.weight" not in state and getattr(config, "tie_word_embeddings", False):
+            state["lm_head.weight"] = state["model.embed_tokens.weight"]
+        state = {k: v for k, v in state.items() if not k.endswith("rotary_emb.inv_freq")}
+        model.load_state_dict(state, strict=True)
+        if torch_dtype is not None:
+            model = model.to(torch_dtype)
+        if device_map is not None:          # "auto" / "cuda" / {"": device}: one replica on the current GPU (dp, not pipeline)
+            model = model.cuda()
+        return model.eval()
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .half() / .cuda() re-create every parameter: the fused decode buffers and the captured graph would keep
+        # pointing at the old storage
+        self._fast, self._graph, self._rope = None, None, None
+        return super()._apply(fn, *args, **kwargs)
 
     # ------------------------------------------------------------------ helpers
     def _tables(self, device):
-        if self._rope is None or self._rope[0].device != device:
+        rows = getattr(self.config, "max_position_embeddings", 4096)
+        if self.cache is not None:
+            rows = max(rows, self.cache.max_tokens + 1)   # a cache longer than the config's context still has its rows
+        if self._rope is None or self._rope[0].device != device or self._rope[0].shape[0] < rows:
             hd = self.config.hidden_size // self.config.num_attention_heads
-            self._rope = _rope_tables(hd, self.config.max_position_embeddings, self.config.rope_theta, device)
+            self._rope = _rope_tables(hd, rows, self.config.rope_theta, device)
         return self._rope
 
     def _run_layers(self, input_ids, positions, pasts, attention_mask=None):
@@ -296,14 +393,57 @@ class LlamaForCausalLM_KIVI(nn.Module):
 
     # ------------------------------------------------------------------ reference-style forward (9-tuples)
     @torch.no_grad()
-    def forward(self, input_ids, past_key_values=None, attention_mask=None):
-        """Returns (logits [B, q_len, vocab] fp32, past_key_values): per-layer 9-tuples as in the reference
-        (models/llama_kivi.py:696-698, :911-916).  Prefill when past_key_values is None."""
+    def forward(self, input_ids=None, past_key_values=None, attention_mask=None, position_ids=None, use_cache=None,
+                return_dict=None, **unused):
+        """models/llama_kivi.py:815-905.  Returns logits [B, q_len, vocab] fp32 (:881) and past_key_values = per-layer
+        9-tuples (:696-698, :911-916); prefill when past_key_values is None.  attention_mask: HF padding mask
+        [B, kv_len] or an additive [B, 1, q_len, kv_len].  The result unpacks as (logits, past_key_values) and has the
+        attributes of CausalLMOutputWithPast; with return_dict=True (or config.use_return_dict) it IS one."""
         B, q_len = input_ids.shape
+        if past_key_values is not None and len(past_key_values) == 0:
+            past_key_values = None
         start = 0 if past_key_values is None else past_key_values[0][-1]
-        positions = torch.arange(start, start + q_len, device=input_ids.device).unsqueeze(0).expand(B, -1)
-        h, pasts = self._run_layers(input_ids, positions, past_key_values, attention_mask)
-        return self.lm_head(h).float(), pasts                                # logits.float() (:881)
+        if position_ids is None:
+            position_ids = torch.arange(start, start + q_len, device=input_ids.device).unsqueeze(0).expand(B, -1)
+        rows = self._tables(input_ids.device)[0].shape[0]
+        if start + q_len > rows:            # the slow path's index_select would raise; say why
+            raise ValueError(f"{start + q_len} positions exceed config.max_position_embeddings = {rows}")
+        dtype = self.lm_head.weight.dtype
+        mask = _additive_mask(attention_mask, q_len, start + q_len, dtype, input_ids.device)
+        h, pasts = self._run_layers(input_ids, position_ids, past_key_values, mask)
+        logits = self.lm_head(h).float()                                     # logits.float() (:881)
+        if return_dict is None:
+            return_dict = getattr(self.config, "use_return_dict", False)
+        if return_dict:
+            from transformers.modeling_outputs import CausalLMOutputWithPast
+            return CausalLMOutputWithPast(loss=None, logits=logits, past_key_values=tuple(pasts))
+        return _Output((logits, pasts))
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None,
+                                      **kwargs):
+        """models/llama_kivi.py:908-948: feed only the tokens the cache has not seen (its length is the last element
+        of a layer's tuple), positions from the padding mask."""
+        if past_key_values is not None and len(past_key_values) == 0:
+            past_key_values = None
+        if past_key_values is not None:
+            seen = past_key_values[0][-1]
+            drop = seen if input_ids.shape[1] > seen else input_ids.shape[1] - 1
+            input_ids = input_ids[:, drop:]
+        position_ids = kwargs.get("position_ids")
+        if attention_mask is not None and position_ids is None:
+            position_ids = attention_mask.long().cumsum(-1) - 1
+            position_ids.masked_fill_(attention_mask == 0, 1)
+            if past_key_values:
+                position_ids = position_ids[:, -input_ids.shape[1]:]
+        return {"input_ids": input_ids, "position_ids": position_ids, "past_key_values": past_key_values,
+                "use_cache": kwargs.get("use_cache"), "attention_mask": attention_mask}
+
+    @staticmethod
+    def _reorder_cache(past_key_values, beam_idx):
+        """models/llama_kivi.py:950-957 (beam search): select batch rows of every tensor of every layer's tuple; the
+        reference's version fails on the None entries and the trailing int of the 9-tuple -- they pass through here."""
+        return tuple(tuple(t.index_select(0, beam_idx.to(t.device)) if torch.is_tensor(t) else t for t in layer_past)
+                     for layer_past in past_key_values)
 
     # ------------------------------------------------------------------ fused cache path
     def init_cache(self, batch: int, max_tokens: int):
@@ -317,6 +457,19 @@ class LlamaForCausalLM_KIVI(nn.Module):
         self._pos = torch.zeros((batch, 1), dtype=torch.long, device=dev)
         self._ids = torch.zeros((batch, 1), dtype=torch.long, device=dev)
         self._logits = torch.zeros((batch, cfg.vocab_size), dtype=torch.float32, device=dev)
+        self.next_tokens = torch.zeros((batch,), dtype=torch.long, device=dev)   # greedy argmax of the step (in-graph)
+        self._tables(dev)                                    # rows for every position the cache can reach
+        return self.cache
+
+    def import_cache(self, past_key_values, max_tokens: int | None = None):
+        """Continue on the fused path from the reference's per-layer 9-tuples (models/llama_kivi.py:454-455)."""
+        seen = past_key_values[0][-1]
+        B = past_key_values[0][5].shape[0]
+        if self.cache is None or self.cache.batch != B or (max_tokens or 0) > self.cache.max_tokens:
+            self.init_cache(B, max_tokens or seen + 1024)
+        for i, past in enumerate(past_key_values):
+            self.cache.import_tuple(i, past)
+        self._pos.fill_(seen)
         return self.cache
 
     @torch.no_grad()
@@ -352,24 +505,60 @@ class LlamaForCausalLM_KIVI(nn.Module):
             self._logits.copy_(self.lm_head(h[:, 0]).float())
         self.cache_advance_device()
         self._pos.add_(1)
+        # greedy sampling inside the step (and inside its CUDA graph): the argmax of a sequence needs only that
+        # sequence's logits, so with data-parallel replicas the exchange is the sampled ids, 8 B per sequence
+        torch.argmax(self._logits, dim=-1, out=self.next_tokens)
+        self._ids.copy_(self.next_tokens.view(-1, 1))        # decode_step() without ids continues with the sampled ones
+        if self._dist_tokens is not None and self._dist_in_graph:
+            from . import dist as kdist
+            kdist.gather_tokens(self.next_tokens, out=self._dist_tokens)
+
+    def enable_token_allgather(self, world_size: int, in_graph: bool = True):
+        """Data-parallel replicas (kivi_b200.dist): gather every rank's sampled ids into `all_tokens`
+        [world_size * B] -- inside the decode step and its CUDA graph (in_graph, the default), or right after the
+        replay.  Call before the first decode_step (the step is captured once)."""
+        self._dist_tokens = torch.zeros(world_size * self.cache.batch, dtype=torch.long, device=self.cache.device) \
+            if world_size > 1 else None
+        self._dist_in_graph = in_graph
+        self._graph = None
+
+    @property
+    def all_tokens(self):
+        return self.next_tokens if self._dist_tokens is None else self._dist_tokens
 
     def _fast_ok(self):
         a = self.model.layers[0].self_attn
         return a.head_dim == 128 and a.q_proj.bias is None and self.lm_head.weight.dtype == torch.float16
 
     def _ensure_fast(self):
-        """Concatenated q|k|v and gate|up weights + static activation buffers for the 9-launch-per-layer step."""
-        if getattr(self, "_fast", None) is not None and self._fast.B == self.cache.batch:
+        """Fused q|k|v, o and gate|up weights in [in, out] layout + static activation buffers for the 9-launch-per-layer
+        step.  At M = B rows cuBLAS streams the weights 9-13 % faster from this layout (tools/gemm_probe.py: q|k|v 27.6 vs
+        31.8 us, o 15.4 vs 17.4 us, gate|up 42.0 vs 46.1 us; down is layout-neutral).  The fused buffers OWN the storage:
+        the nn.Linear parameters become transposed views of them, so there is one copy of every weight (the reference's
+        mem_spd_test reports peak memory) and load_state_dict / in-place edits reach the decode path."""
+        if self._fast is not None and self._fast.B == self.cache.batch:
             return self._fast
         cfg, dev, B = self.config, self.cache.device, self.cache.batch
         H, Hkv, hid, inter = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.hidden_size, cfg.intermediate_size
-        f = SimpleNamespace(B=B)
-        # decode-time copies in [in, out] layout: at M = B rows cuBLAS streams the weights 9-13 % faster from this layout
-        # (tools/gemm_probe.py: q|k|v 27.6 vs 31.8 us, o 15.4 vs 17.4 us, gate|up 42.0 vs 46.1 us; down is layout-neutral)
-        f.wqkv = [torch.cat([l.self_attn.q_proj.weight, l.self_attn.k_proj.weight, l.self_attn.v_proj.weight], 0).t().contiguous()
-                  for l in self.model.layers]
-        f.wgu = [torch.cat([l.mlp.gate_proj.weight, l.mlp.up_proj.weight], 0).t().contiguous() for l in self.model.layers]
-        f.wo = [l.self_attn.o_proj.weight.t().contiguous() for l in self.model.layers]
+        f = self._fast if self._fast is not None else SimpleNamespace(wqkv=None)
+        f.B = B
+        if f.wqkv is None:
+            def view_param(buf, lo, hi):
+                return nn.Parameter(buf.t()[lo:hi], requires_grad=False)
+            f.wqkv, f.wgu, f.wo = [], [], []
+            for l in self.model.layers:
+                a, m = l.self_attn, l.mlp
+                nq, nk = a.q_proj.weight.shape[0], a.k_proj.weight.shape[0]
+                w = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).t().contiguous()
+                a.q_proj.weight, a.k_proj.weight = view_param(w, 0, nq), view_param(w, nq, nq + nk)
+                a.v_proj.weight = view_param(w, nq + nk, w.shape[1])
+                f.wqkv.append(w)
+                w = torch.cat([m.gate_proj.weight, m.up_proj.weight], 0).t().contiguous()
+                m.gate_proj.weight, m.up_proj.weight = view_param(w, 0, inter), view_param(w, inter, 2 * inter)
+                f.wgu.append(w)
+                w = a.o_proj.weight.t().contiguous()
+                a.o_proj.weight = view_param(w, 0, w.shape[1])
+                f.wo.append(w)
         e = lambda *shape: torch.empty(shape, dtype=torch.float16, device=dev)  # noqa: E731
         f.res, f.h, f.o, f.d = e(B, hid), e(B, hid), e(B, hid), e(B, hid)
         f.qkv, f.q, f.k, f.v = e(B, (H + 2 * Hkv) * 128), e(B, H, 128), e(B, Hkv, 128), e(B, Hkv, 128)
@@ -413,8 +602,9 @@ class LlamaForCausalLM_KIVI(nn.Module):
     @torch.no_grad()
     def decode_step(self, input_ids=None, use_graph: bool = True):
         """One decode step for the whole batch: input_ids [B, 1] (device) -> logits [B, vocab] fp32 (device,
-        a static buffer).  The step (32 x [norm, qkv, rope, fused KIVI attention, o_proj, MLP], lm_head,
-        cache advance) is captured once in a CUDA graph and replayed."""
+        a static buffer); `next_tokens` [B] holds their argmax (and `all_tokens` every rank's, see
+        enable_token_allgather).  The step (32 x [norm, qkv, rope, fused KIVI attention, o_proj, MLP], lm_head,
+        cache advance, greedy argmax, token all-gather) is captured once in a CUDA graph and replayed."""
         assert self.cache is not None
         if self.cache.kv_len + 1 > self.cache.max_tokens:
             raise ValueError("KIVI cache capacity exceeded")
@@ -424,22 +614,21 @@ class LlamaForCausalLM_KIVI(nn.Module):
             self._step_body()
         else:
             if self._graph is None:
-                # warm-up on a side stream (cuBLAS workspaces, lazy module loading), then capture
+                # warm-up on a side stream (cuBLAS workspaces, lazy module loading, NCCL channels), then capture
                 state = self.cache.state.clone()
-                pos = self._pos.clone()
-                snap = [[b.clone() for b in (bufs[2], bufs[3])] for bufs in self.cache._bufs]  # fp16 windows
+                pos, ids0 = self._pos.clone(), self._ids.clone()
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     self._step_body()
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
-                # undo the warm-up step's effect on the lengths (data it wrote lies beyond them)
+                # undo the warm-up step's effect on the lengths.  Everything it wrote lies BEYOND them -- the new token's
+                # window slots (K slot r, the free slot of the V ring), a flushed K block past tk, the packed V token at
+                # tv -- and is rewritten with the same bytes by the first replayed step.
                 self.cache.state.copy_(state)
                 self._pos.copy_(pos)
-                for bufs, (kr, vr) in zip(self.cache._bufs, snap):
-                    bufs[2].copy_(kr)
-                    bufs[3].copy_(vr)
+                self._ids.copy_(ids0)
                 from . import _lib
                 n0 = _lib.launch_count()
                 g = torch.cuda.CUDAGraph()
@@ -449,22 +638,38 @@ class LlamaForCausalLM_KIVI(nn.Module):
                 # capture does not execute: state is still the pre-step state
                 self._graph = g
             self._graph.replay()
+        if self._dist_tokens is not None and not self._dist_in_graph:
+            from . import dist as kdist
+            kdist.gather_tokens(self.next_tokens, out=self._dist_tokens)
         self.cache._mirror_advance()
         return self._logits
 
     @torch.no_grad()
-    def generate(self, input_ids, max_new_tokens: int, use_graph: bool = True):
-        """Greedy decoding (the reference goes through HF generate; sampling is outside the hot path)."""
+    def generate(self, input_ids=None, max_new_tokens: int | None = None, use_graph: bool = True, attention_mask=None,
+                 max_length: int | None = None, do_sample: bool = False, **unused):
+        """Greedy decoding on the fused path with the call shape of HF generate (`model.generate(**inputs,
+        max_new_tokens=n)`, example.py:60-61, mem_spd_test.py:66): returns [B, prompt + new] ids.  Sampling is outside
+        the hot path: do_sample is rejected; a padding mask must be all ones (equal-length prompts, as everywhere the
+        reference's cache keeps ONE kv_seq_len per batch, :309, :455)."""
+        if do_sample:
+            raise NotImplementedError("kivi_b200.generate decodes greedily; sample from decode_step() logits instead")
+        if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
+            raise NotImplementedError("padded prompts: use forward() with the 9-tuple cache (mask support) instead")
         B, n = input_ids.shape
-        if self.cache is None:
+        if max_new_tokens is None:
+            if max_length is None:
+                raise ValueError("generate() needs max_new_tokens or max_length")
+            max_new_tokens = max_length - n
+        if self.cache is None or self.cache.batch != B or self.cache.max_tokens < n + max_new_tokens:
             self.init_cache(B, n + max_new_tokens)
         logits = self.prefill(input_ids)
         out = [input_ids]
         tok = logits.argmax(-1, keepdim=True)
-        for _ in range(max_new_tokens):
+        for _ in range(max_new_tokens - 1):
             out.append(tok)
-            logits = self.decode_step(tok, use_graph=use_graph)
-            tok = logits.argmax(-1, keepdim=True)
+            self.decode_step(tok, use_graph=use_graph)
+            tok = self.next_tokens.view(B, 1).clone()
+        out.append(tok)
         return torch.cat(out, dim=1)
 
 

@@ -136,3 +136,68 @@ def test_cache_struct_mirrors_the_header():
     assert flag == 1                                                  # KiviCache(overlap_prologue=True) stores 1 in `flags`
     src = inspect.getsource(cache.KiviCache.__init__)
     assert "1 if overlap_prologue else 0" in src
+    shift = int(re.search(r"#define KIVI_CACHE_GQA_CHUNK_SHIFT\s+(\d+)", txt).group(1))
+    assert shift == 4 and "int(gqa_chunk) << 4" in src
+
+
+def test_reference_import_paths_resolve_here():
+    """models/llama_kivi.py:9-10 does `from quant.new_pack import triton_quantize_and_pack_along_last_dim` and
+    `from quant.matmul import cuda_bmm_fA_qB_outer`; quant/matmul.py:6 does `import kivi_gemv`; example.py:4 /
+    mem_spd_test.py:4 do `from models.llama_kivi import LlamaForCausalLM_KIVI`.  The same statements work in this
+    repository and land on kivi_b200."""
+    import kivi_gemv
+    from models.llama_kivi import LlamaForCausalLM_KIVI
+    from models.mistral_kivi import MistralForCausalLM_KIVI
+    from quant.gemv import dequant_weight_outer, gemv_fwd
+    from quant.matmul import cuda_bmm_fA_qB_outer, triton_bmm_fA_qB_outer
+    from quant.new_pack import triton_quantize_and_pack_along_last_dim, unpack_and_dequant_vcache
+    import kivi_b200.kivi_gemv
+    import kivi_b200.llama_kivi
+    import kivi_b200.matmul
+    import kivi_b200.new_pack
+    assert triton_quantize_and_pack_along_last_dim is kivi_b200.new_pack.triton_quantize_and_pack_along_last_dim
+    assert cuda_bmm_fA_qB_outer is kivi_b200.matmul.cuda_bmm_fA_qB_outer
+    assert triton_bmm_fA_qB_outer is kivi_b200.matmul.triton_bmm_fA_qB_outer
+    assert kivi_gemv.gemv_forward_cuda_outer_dim is kivi_b200.kivi_gemv.gemv_forward_cuda_outer_dim
+    assert LlamaForCausalLM_KIVI is kivi_b200.llama_kivi.LlamaForCausalLM_KIVI is MistralForCausalLM_KIVI
+    assert callable(unpack_and_dequant_vcache) and callable(gemv_fwd) and callable(dequant_weight_outer)
+
+
+def test_model_class_contract_on_cpu(tmp_path):
+    """LlamaForCausalLM_KIVI keeps the reference's class contract (models/llama_kivi.py:785-957) where no GPU is
+    needed: from_pretrained on a local checkpoint directory, HF parameter names, prepare_inputs_for_generation
+    (:908-948) and _reorder_cache (:950-957) on 9-tuples."""
+    import json
+    import torch
+    from safetensors.torch import save_file
+    from kivi_b200.llama_kivi import LlamaForCausalLM_KIVI, default_config
+    cfg = default_config("tiny")
+    torch.manual_seed(0)
+    src = LlamaForCausalLM_KIVI(cfg)
+    save_file({k: v.contiguous() for k, v in src.state_dict().items()}, str(tmp_path / "model.safetensors"))
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump({k: v for k, v in vars(cfg).items() if k not in ("k_bits", "v_bits", "group_size", "residual_length")}, f)
+    m = LlamaForCausalLM_KIVI.from_pretrained(str(tmp_path), torch_dtype=torch.float16)
+    assert (m.config.k_bits, m.config.v_bits, m.config.group_size, m.config.residual_length) == (2, 2, 32, 128)
+    assert m.lm_head.weight.dtype == torch.float16
+    for k, v in src.state_dict().items():
+        assert torch.equal(m.state_dict()[k], v.half()), k
+    assert "model.layers.0.self_attn.q_proj.weight" in m.state_dict() and "model.norm.weight" in m.state_dict()
+    with pytest.raises(FileNotFoundError):
+        LlamaForCausalLM_KIVI.from_pretrained("meta-llama/Llama-2-7b-hf")          # no network: local directories only
+    # generation plumbing on the reference's 9-tuple (Kq, K_full, K_scale, K_mn, Vq, V_full, V_scale, V_mn, kv_seq_len)
+    B = 3
+    past = tuple((torch.zeros(B, 2, 128, 8, dtype=torch.int32), None, torch.zeros(B, 2, 128, 4), torch.zeros(B, 2, 128, 4),
+                  None, torch.arange(B * 2 * 5 * 128, dtype=torch.float32).view(B, 2, 5, 128), None, None, 133)
+                 for _ in range(2))
+    ids = torch.arange(B * 134).view(B, 134)
+    mask = torch.ones(B, 134, dtype=torch.long)
+    mask[1, :4] = 0                                                                # a left-padded row
+    inp = m.prepare_inputs_for_generation(ids, past_key_values=past, attention_mask=mask)
+    assert inp["input_ids"].shape == (B, 1) and torch.equal(inp["input_ids"][:, 0], ids[:, -1])
+    assert inp["position_ids"].tolist() == [[133], [129], [133]] and inp["past_key_values"] is past
+    first = m.prepare_inputs_for_generation(ids, past_key_values=None, attention_mask=mask)
+    assert first["input_ids"].shape == (B, 134) and first["position_ids"][1, :6].tolist() == [1, 1, 1, 1, 0, 1]
+    re_ = LlamaForCausalLM_KIVI._reorder_cache(past, torch.tensor([2, 0, 0]))
+    assert len(re_) == 2 and re_[0][8] == 133 and re_[0][1] is None
+    assert torch.equal(re_[1][5], past[1][5][[2, 0, 0]])

@@ -30,6 +30,11 @@ def _worker(rank, ws, port, gb, out_dir):
     assert torch.equal(toks, full.argmax(-1)) and torch.equal(mine, full.argmax(-1)[lo:hi])
     g = kdist.gather_logits(local, gb)
     assert torch.equal(g, full)
+    if gb % ws == 0:                                             # the greedy path: only the sampled ids travel
+        allt = kdist.gather_tokens(local.argmax(-1))
+        assert torch.equal(allt, full.argmax(-1))
+        buf = torch.empty(gb, dtype=torch.long)
+        assert kdist.gather_tokens(local.argmax(-1), out=buf) is buf and torch.equal(buf, full.argmax(-1))
     m = kdist.max_over_ranks(float(rank + 1))
     assert m == float(ws)
     kdist.barrier()

@@ -153,3 +153,23 @@ def test_pack_full_size_properties(bits, g, shape):
     rc, rs, rm = ref.pack_lastdim(sl, g, bits)
     gc = to_np(code[1, 2]) if shape[2] > 1 else to_np(code[1, :4, 0])
     np.testing.assert_array_equal(gc, rc)
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8])
+@pytest.mark.parametrize("g", [32, 64])
+def test_torch_gpu_checker_is_pinned_to_the_oracle(bits, g):
+    """oracle/torch_ref.pack_lastdim (the reference's ATen chain on this GPU, used as the full-size checker in
+    tests/test_reference_cases_gpu.py) == the C oracle (pinned to the reference's Python by tests/golden/), bit for bit,
+    including flat groups (0/0 -> NaN -> code 0) and the dequant chain."""
+    from oracle import ref, torch_ref
+    rng = np.random.default_rng(bits * 100 + g)
+    x = (rng.standard_normal((3, 5, 17, 256)) * rng.choice([0.01, 1.0, 30.0], size=(3, 5, 17, 1))).astype(np.float16)
+    x[0, 0, 0, :g] = np.float16(0.37)                                       # a flat group
+    x[1, 2, 3, g:2 * g] = 0
+    c, s, m = torch_ref.pack_lastdim(torch.from_numpy(x).cuda(), g, bits)
+    ec, es, em = ref.pack_lastdim(x, g, bits)
+    np.testing.assert_array_equal(to_np(c), ec)
+    np.testing.assert_array_equal(to_np(s).view(np.uint16), es.view(np.uint16))
+    np.testing.assert_array_equal(to_np(m).view(np.uint16), em.view(np.uint16))
+    d = torch_ref.unpack_dequant_lastdim(c, s, m, g, bits)
+    np.testing.assert_array_equal(to_np(d).view(np.uint16), ref.unpack_dequant_lastdim(ec, es, em, g, bits).view(np.uint16))
