@@ -175,12 +175,21 @@ __device__ __forceinline__ float fast_exp(float x) {
 __device__ __forceinline__ uint32_t h2_as_u32(const __half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u32_as_h2(const uint32_t u) { return *reinterpret_cast<const __half2*>(&u); }
 
-// One B-fragment register: column part 0 -> hi = fp16(x*s); part 1 -> lo = x*s - hi (exact).  Branch-free:
-// nh = hi * (part ? -1 : 0);  b = fma(x, s, nh).
+// One B-fragment register: column part 0 -> hi = fp16(x*s); part 1 -> lo = x*s - hi (exact: the residual of an fp16
+// product is an fp16).
+#ifndef KIVI_BPREP2
+#define KIVI_BPREP2 1                    // 1: hi, then a PREDICATED fma(x, s, -hi) in the lo lanes (2 instructions); 0: branch-free 3
+#endif
 __device__ __forceinline__ uint32_t b_prep(uint32_t x2, uint32_t s2, __half2 msel) {
     const __half2 x = u32_as_h2(x2), s = u32_as_h2(s2);
-    const __half2 nh = __hmul2(__hmul2(x, s), msel);
+#if KIVI_BPREP2
+    __half2 b = __hmul2(x, s);
+    if (h2_as_u32(msel) != 0u) b = __hfma2(x, s, __hneg2(b));   // lane-invariant predicate, negation folds into the HFMA2 operand
+    return h2_as_u32(b);
+#else
+    const __half2 nh = __hmul2(__hmul2(x, s), msel);         // nh = hi * (part ? -1 : 0);  b = fma(x, s, nh)
     return h2_as_u32(__hfma2(x, s, nh));
+#endif
 }
 
 // exact power of two 2^(24 - P) that undoes the denormal scaling of the fields of MMA mm
@@ -714,41 +723,30 @@ qk_kernel(const AttnParams p)
                 const int64_t rowi = uq0 + h_l;
                 __half* row = p.w.lg + rowi * p.w.ld + j * kBlockTokens;
                 const int nvalid = s.tk - j * kBlockTokens;                  // < 128 only in the last block when R < 128
+                // the lane's logits by compile-time slot; slots of MMAs this lane does not own and tokens past the packed
+                // length stay -inf.  ONE arithmetic for the production and the instrumented / masked / partial-block
+                // epilogues (same fold order, hence bit-identical statistics): they differ only in predicated side work.
+                float x[Slots<G, GS>::k];
+                #pragma unroll
+                for (int e = 0; e < Slots<G, GS>::k; ++e) x[e] = -INFINITY;
                 if (!slow && nvalid >= kBlockTokens) {
-                    {                                                        // the lane's logits by compile-time slot
-                        float x[Slots<G, GS>::k];
-                        #pragma unroll
-                        for (int e = 0; e < Slots<G, GS>::k; ++e) x[e] = -INFINITY;  // slots of MMAs this lane does not own
-                        finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int o, float v) {
-                            const __half hv = scale_logit(v);
-                            row[o] = hv;
-                            x[slot] = __half2float(hv);
-                        });
-                        fold_stats(m_blk, s_blk, x);
-                    }
+                    finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int o, float v) {
+                        const __half hv = scale_logit(v);
+                        row[o] = hv;
+                        x[slot] = __half2float(hv);
+                    });
                 } else {
-                    auto logit_of = [&](int o, float v) -> __half {          // fp16 scaled (+ mask): the softmax input
-                        __half hv = scale_logit(v);
-                        if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + j * kBlockTokens + o);
-                        return hv;
-                    };
-                    float mx = m_blk;
-                    finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
+                    finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int slot, int o, float v) {
                         if (o < nvalid) {
-                            const __half hv = logit_of(o, v);
+                            __half hv = scale_logit(v);                      // fp16 scaled (+ mask): the softmax input
+                            if (p.mask) hv = apply_mask(hv, p.mask, (int64_t)b * s.T + j * kBlockTokens + o);
                             row[o] = hv;
                             if (p.dbg_logits) p.dbg_logits[rowi * p.dbg_stride + j * kBlockTokens + o] = hv;
-                            mx = fmaxf(mx, __half2float(hv));
+                            x[slot] = __half2float(hv);
                         }
                     });
-                    if (mx != -INFINITY) {
-                        float a2 = s_blk * fast_exp(m_blk - mx);
-                        finalize<KB, G, GS>(acc, zsel, lane, 1.f, [&](int, int o, float v) {
-                            if (o < nvalid) a2 += fast_exp(__half2float(logit_of(o, v)) - mx);
-                        });
-                        m_blk = mx; s_blk = a2;
-                    }
                 }
+                fold_stats(m_blk, s_blk, x);
             } else if (j < s.ipu - 1) {                                      // ---- fp16 K window item (tensor cores)
                 // D[head][token] = sum_ch q_h[ch] * K[token][ch]: A = q (rows = heads, exact fp16), B = the window rows as they
                 // lie in the stage ([token][channel], swizzled units -> conflict-free fragment loads), 2 tiles of 8 tokens
@@ -925,7 +923,6 @@ sv_kernel(const AttnParams p)
     Cursor cur;
     cur.unit = lo / s.bpu; cur.j = lo - cur.unit * s.bpu; cur.half = 0; cur.left = hi - lo;
     pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
-    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
     const int h_l = t4 % G;
@@ -948,7 +945,10 @@ sv_kernel(const AttnParams p)
             if (lane < nstat) sn[h] = __ldcg(p.w.stats + (int64_t)(row0 + h) * p.w.stat_cap + lane);
         }
     };
+    // the few statistics words first, THEN the bulk copies: every warp of the grid issues its first stages at this very
+    // moment (~29 MB in flight), and a small load queued behind them would be the last thing to arrive
     fetch_stats(unit);
+    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
     KIVI_TL(1, gw, 1);
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
     CommitIn pend_cin;

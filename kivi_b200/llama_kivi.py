@@ -449,6 +449,7 @@ class LlamaForCausalLM_KIVI(nn.Module):
     def init_cache(self, batch: int, max_tokens: int):
         cfg = self.config
         dev = self.lm_head.weight.device
+        self.cache, self._graph = None, None                 # release the previous cache before the new one is allocated
         self.cache = KiviCache(cfg.num_hidden_layers, batch, cfg.num_attention_heads, cfg.num_key_value_heads,
                                cfg.hidden_size // cfg.num_attention_heads, cfg.k_bits, cfg.v_bits, cfg.group_size,
                                cfg.residual_length, max_tokens, device=dev,

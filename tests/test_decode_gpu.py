@@ -491,10 +491,15 @@ def test_import_tuple_roundtrip(B, H, Hkv, kb, vb, g, R, n0, steps):
             assert tup_b[i] is None
         else:
             assert torch.equal(tup[i], tup_b[i]), f"tuple[{i}]"
-    for _ in range(R + 3):                                           # continue on both: same bits, flushes included
+    for _ in range(R + 3):                                           # continue on both, flushes included
         q, kn, vn = mk(B, H, 128), mk(B, Hkv, 128), mk(B, Hkv, 128)
         oa, ob = a.decode_attention(0, q, kn, vn), b.decode_attention(0, q, kn, vn)
-        assert torch.equal(oa, ob)
+        # same cache CONTENTS, but the imported V ring starts at slot 0: its 16-token window items are cut at other
+        # places, so the fp32 partial sums are added in another order (bit-equal only when the ring heads coincide)
+        if a.vhead == b.vhead:
+            assert torch.equal(oa, ob)
+        err = (oa.float() - ob.float()).abs()
+        assert bool((err <= 1e-3 * oa.float().abs() + 1e-3 * float(oa.float().abs().max())).all()), float(err.max())
         a.advance(), b.advance()
     ta, tb = a.export(0), b.export(0)
     for i in range(8):
