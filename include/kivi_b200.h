@@ -205,6 +205,11 @@ int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* q, const vo
                               const void* mask, void* out, void* workspace, int64_t workspace_bytes,
                               void* dbg_logits, void* dbg_probs, int64_t dbg_stride, int max_kv_len, void* stream);
 
+/* Test hook: the (unit, item) work split of the two decode kernels evaluated on the host (kernel 0 = q.K^T, 1 = p.V cost
+ * model); a unit has n_b packed blocks, n_w window items and the new token.  out_lo: 2 * (W + 1) ints, (unit, item) of the first
+ * position of every range and of the end; out_owner: NULL or one int per position.  Returns the number of ranges W. */
+int kivi_debug_range_split(int n_units, int n_b, int n_w, int w_cap, int kernel, int* out_lo, int* out_owner);
+
 /* Advance `state` by one token (the bookkeeping of :343-356, :386-399); once per step, all layers. */
 int kivi_cache_advance(const kivi_cache_t* cache, void* stream);
 

@@ -40,6 +40,7 @@ const Tuning& tuning()
         v.ctas_per_sm = geti("KIVI_CTAS_PER_SM");
         v.stages_per_warp = geti("KIVI_STAGES_PER_WARP");
         v.no_pdl = getenv("KIVI_NO_PDL") != nullptr;
+        v.no_mma_gemv = getenv("KIVI_NO_MMA_GEMV") != nullptr;       // A/B: SIMT kernels only (tools/microbench.py)
         return v;
     }();
     return t;

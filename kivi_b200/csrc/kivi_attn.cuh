@@ -448,9 +448,10 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
     if (s.r + 1 < c.R) {
         if (lane >= 16) reinterpret_cast<uint4*>(c.k_res + (int64_t)u * c.R * kD)[win_unit(s.r, lane - 16)] = knew4;
     } else {
-        // once per R steps.  A lane owns channels d = lane + 32 i.  Per channel the 16 * kSlabs half-words (row = token % 16 of
-        // a slab) of the destination block are assembled in registers: per group of g tokens, 32 values at a time (independent
-        // loads), min / max, then each chunk of 16 consecutive tokens fills ONE field position j of the 16 half-words.
+        // once per R steps.  lane = (hw, cu): token parity hw = lane >> 4, channels 8 cu .. 8 cu + 7 (cu = lane & 15): every
+        // window row is read with 128-bit loads (a lane's 16-byte unit of the swizzled row), twice per group (min / max, then
+        // codes).  A lane then owns whole 32-bit words of the destination block -- the channel pairs (8 cu + 2q, + 1), the
+        // rows 2m + hw of a slab, all their fields -- assembled in registers and stored once per slab.
         constexpr int F = 16 / KB, kSlabRows = 16 * F, kSlabs = 128 / kSlabRows;
         const float maxq = (float)((1 << KB) - 1);
         const int bb = lay_block_bytes(KB, g);
@@ -459,62 +460,102 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
         const __half* knew = p.k_new + (int64_t)u * kD;
         const int nblk = max(1, c.R / kBlockTokens);                                    // R in {32, 64, 128, 256}
         const int cnt = min(c.R, kBlockTokens);                                         // flushed tokens per destination block
+        const int hw = lane >> 4, cu = lane & 15;
+        auto row8 = [&](int t) -> uint4 {                                               // window token t, channels 8 cu .. + 7
+            return t < c.R - 1 ? __ldcg(reinterpret_cast<const uint4*>(win + (int64_t)t * kD) + (cu ^ (t & 7)))
+                               : __ldg(reinterpret_cast<const uint4*>(knew) + cu);
+        };
+        // word (q, m) of slab sl: inner pair 8 cu + 2q (+1), row 2m + hw  (kivi_decode.cuh: lane' = (row & 7) * 4 + q, r = 2 (cu & 1) + (row >> 3))
+        auto word_ptr = [&](uint8_t* blk, int sl, int q, int m) -> uint32_t* {
+            const int row = 2 * m + hw;
+            return reinterpret_cast<uint32_t*>(blk) + (((cu >> 1) * kSlabs + sl) * 128 + ((row & 7) * 4 + q) * 4 + (cu & 1) * 2 + (row >> 3));
+        };
         #pragma unroll 1
         for (int bi = 0; bi < nblk; ++bi) {
             const int tb = s.tk + bi * kBlockTokens;                                    // first flushed token of this block
             const int o0 = tb % kBlockTokens;                                           // its outer index (multiple of R)
             uint8_t* blk = ub + (int64_t)(tb / kBlockTokens) * bb;
-            #pragma unroll 1
-            for (int d = lane; d < kD; d += 32) {
-                uint32_t hw[kSlabs * 16];
-                const bool partial = cnt < kBlockTokens;                                // other fields of the half-words are live data
+            const bool partial = cnt < kBlockTokens;                                    // other fields of the words are live data
+            uint32_t words[4][8];
+            int cur_sl = -1;
+            auto store_slab = [&]() {
                 #pragma unroll
-                for (int i = 0; i < kSlabs * 16; ++i)
-                    hw[i] = partial ? *reinterpret_cast<const uint16_t*>(blk + lay_word_off(KB, d, (i >> 4) * kSlabRows + (i & 15)) + 2 * (d & 1)) : 0u;
+                for (int q = 0; q < 4; ++q)
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) *word_ptr(blk, cur_sl, q, m) = words[q][m];
+            };
+            #pragma unroll 1
+            for (int gl = 0; gl < cnt / g; ++gl) {                                      // groups landing in this block
+                const int tl0 = bi * kBlockTokens + gl * g;                             // first token of the group within the window
+                float mnf[8], mxf[8];
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) { mnf[e] = INFINITY; mxf[e] = -INFINITY; }
                 #pragma unroll 1
-                for (int gl = 0; gl < cnt / g; ++gl) {                                  // groups landing in this block
-                    const int tl0 = bi * kBlockTokens + gl * g;                         // first token of the group within the window
-                    float mnf = INFINITY, mxf = -INFINITY;
-                    #pragma unroll 1
-                    for (int i0 = 0; i0 < g; i0 += 32) {
-                        float x[32];
+                for (int i0 = 0; i0 < g; i0 += 16) {                                    // 8 rows of this parity per pass (independent loads)
+                    uint4 v[8];
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) v[m] = row8(tl0 + i0 + 2 * m + hw);
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&v[m]);
                         #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int t = tl0 + i0 + i;
-                            x[i] = __half2float(t < c.R - 1 ? win[win_off(t, d)] : knew[d]);
-                        }
-                        #pragma unroll
-                        for (int i = 0; i < 32; ++i) { mnf = fminf(mnf, x[i]); mxf = fmaxf(mxf, x[i]); }
-                    }
-                    const __half d16 = __float2half_rn(mxf - mnf);
-                    const __half sc = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
-                    const float scf = __half2float(sc);
-                    const int og = o0 + gl * g;                                         // outer index of the group's first token
-                    *reinterpret_cast<__half*>(blk + lay_scale_off(KB, g, d, og / g)) = sc;
-                    *reinterpret_cast<__half*>(blk + lay_zero_off(KB, g, d, og / g)) = __float2half_rn(mnf);
-                    #pragma unroll 1
-                    for (int q16 = 0; q16 < g / 16; ++q16) {
-                        const int o = og + 16 * q16;                                    // outer index of row 0 of this 16-token chunk
-                        const int sl = o / kSlabRows, j = (o % kSlabRows) / 16;
-                        float x[16];
-                        #pragma unroll
-                        for (int row = 0; row < 16; ++row) {
-                            const int t = tl0 + 16 * q16 + row;
-                            x[row] = __half2float(t < c.R - 1 ? win[win_off(t, d)] : knew[d]);
-                        }
-                        #pragma unroll
-                        for (int row = 0; row < 16; ++row) {
-                            const uint32_t code = (uint32_t)__float2int_rn(q_code(x[row], mnf, scf, maxq));
-                            #pragma unroll
-                            for (int ss = 0; ss < kSlabs; ++ss)                         // compile-time register index, run-time slab
-                                if (ss == sl) hw[ss * 16 + row] = (hw[ss * 16 + row] & ~(((1u << KB) - 1u) << (KB * j))) | (code << (KB * j));
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __half22float2(h2[q]);
+                            mnf[2 * q] = fminf(mnf[2 * q], f.x); mxf[2 * q] = fmaxf(mxf[2 * q], f.x);
+                            mnf[2 * q + 1] = fminf(mnf[2 * q + 1], f.y); mxf[2 * q + 1] = fmaxf(mxf[2 * q + 1], f.y);
                         }
                     }
                 }
+                float scf[8];
+                const int og = o0 + gl * g;                                             // outer index of the group's first token
+                __half sc16[8], mn16[8];
                 #pragma unroll
-                for (int i = 0; i < kSlabs * 16; ++i)
-                    *reinterpret_cast<uint16_t*>(blk + lay_word_off(KB, d, (i >> 4) * kSlabRows + (i & 15)) + 2 * (d & 1)) = (uint16_t)hw[i];
+                for (int e = 0; e < 8; ++e) {
+                    mnf[e] = fminf(mnf[e], __shfl_xor_sync(0xffffffffu, mnf[e], 16));   // the other token parity
+                    mxf[e] = fmaxf(mxf[e], __shfl_xor_sync(0xffffffffu, mxf[e], 16));
+                    const __half d16 = __float2half_rn(mxf[e] - mnf[e]);
+                    sc16[e] = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
+                    scf[e] = __half2float(sc16[e]);
+                    mn16[e] = __float2half_rn(mnf[e]);
+                }
+                if (hw == 0) {
+                    // meta entry of (chunk cu >> 1, group og / g, t = q): { z[2q], z[2q+1], s[2q], s[2q+1] } of the lane's half (cu & 1)
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        __align__(8) __half mz[4] = {mn16[2 * q], mn16[2 * q + 1], sc16[2 * q], sc16[2 * q + 1]};
+                        *reinterpret_cast<uint2*>(blk + lay_zero_off(KB, g, 8 * cu + 2 * q, og / g)) = *reinterpret_cast<const uint2*>(mz);
+                    }
+                }
+                #pragma unroll 1
+                for (int q16 = 0; q16 < g / 16; ++q16) {
+                    const int o = og + 16 * q16;                                        // outer index of row 0 of this 16-token chunk
+                    const int sl = o / kSlabRows, j = (o % kSlabRows) / 16;
+                    if (sl != cur_sl) {
+                        if (cur_sl >= 0) store_slab();
+                        cur_sl = sl;
+                        #pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            #pragma unroll
+                            for (int m = 0; m < 8; ++m) words[q][m] = partial ? *word_ptr(blk, sl, q, m) : 0u;
+                    }
+                    uint4 v[8];
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) v[m] = row8(tl0 + 16 * q16 + 2 * m + hw);
+                    const uint32_t keep = ~((((1u << KB) - 1u) * 0x00010001u) << (KB * j));
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&v[m]);
+                        #pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __half22float2(h2[q]);
+                            const uint32_t c0 = (uint32_t)__float2int_rn(q_code(f.x, mnf[2 * q], scf[2 * q], maxq));
+                            const uint32_t c1 = (uint32_t)__float2int_rn(q_code(f.y, mnf[2 * q + 1], scf[2 * q + 1], maxq));
+                            words[q][m] = (words[q][m] & keep) | ((c0 | (c1 << 16)) << (KB * j));
+                        }
+                    }
+                }
             }
+            if (cur_sl >= 0) store_slab();
         }
     }
 }
@@ -540,16 +581,66 @@ __device__ __forceinline__ __half apply_mask(__half v, const __half* mask, int64
 }
 
 // ------------------------------------------------------------------------------------------------
-// work split: the (unit, pseudo-block) sequence of the whole job, gb = unit * per_unit + j, is cut into one
-// contiguous range per warp: warp w of the W range owners handles [lo(w), lo(w+1)), lo(w) = floor(w * N / W).
-// W <= N, so every range is non-empty and a unit of L pseudo-blocks meets at most ceil(L * W / N) + 1 ranges.
+// work split: the (unit, item) sequence of the whole job -- per unit: n_b packed blocks, n_w fp16 window items, the new
+// token -- is cut into one contiguous range per warp of equal COST.  Costs are small integers per item kind; the first item of
+// a unit may also carry the cost of a (warp, unit) visit (statistics / partial record / arrival).
+//   key(pos)  = cost of everything before position pos = unit * Cu + kj(j)            (exclusive prefix, non-decreasing)
+//   owner(pos) = floor(key(pos) * W / Ctot);   lo(w) = min{pos : key(pos) >= ceil(w * Ctot / W)}
+// W is capped at Ctot / (largest item cost), so every range is non-empty, and a unit meets at most ceil(W / n_units) + 1
+// ranges (the bound the workspace slots are sized for).
+// DEFAULT: every item costs 1 (equal item counts).  A model fitted to the per-warp timeline of the cfg-2 layer (tools/timeline.py:
+// q.K^T window item 0.7, new token 0.1, visit 0.6 blocks; p.V 0.4 / 1.2 / 1.2) does flatten the MODELLED cost -- the q.K^T
+// lifetime spread drops from 2.1 to 1.2 us -- but the kernels get slower (cfg 2 +2 %, cfg 3 +7 %, profiles/r02_range_costs.txt):
+// the tail is set by a few outlier warps (finalisations, L2-far SMs), not by the composition of the ranges.  -DKIVI_UNIFORM_RANGES=0
+// builds the weighted split.
 // ------------------------------------------------------------------------------------------------
-struct Ranges {                         // N pseudo-blocks over W owners; 32-bit arithmetic whenever (N + 1) * W fits
-    unsigned N, W; bool small;
-    __device__ __forceinline__ Ranges(long long n, long long w) : N((unsigned)n), W((unsigned)w), small((n + 1) * w < (1ll << 32)) {}
-    __device__ __forceinline__ int lo(int w) const { return small ? (int)((unsigned)w * N / W) : (int)((long long)w * N / W); }
-    __device__ __forceinline__ int owner(int gb) const {
-        return small ? (int)((((unsigned)gb + 1u) * W - 1u) / N) : (int)((((long long)gb + 1) * W - 1) / N);
+#ifndef KIVI_UNIFORM_RANGES
+#define KIVI_UNIFORM_RANGES 1
+#endif
+struct CostQK { static constexpr unsigned cb = KIVI_UNIFORM_RANGES ? 1 : 16, cw = KIVI_UNIFORM_RANGES ? 1 : 10,
+                                          cn = KIVI_UNIFORM_RANGES ? 1 : 2, cv = KIVI_UNIFORM_RANGES ? 0 : 12; };
+struct CostSV { static constexpr unsigned cb = KIVI_UNIFORM_RANGES ? 1 : 16, cw = KIVI_UNIFORM_RANGES ? 1 : 3,
+                                          cn = KIVI_UNIFORM_RANGES ? 1 : 12, cv = KIVI_UNIFORM_RANGES ? 0 : 35; };
+
+template <class C>
+struct Ranges {
+    int n_b, n_w, per_unit;
+    unsigned Cu, W; unsigned long long Ctot; bool small;
+    __host__ __device__ __forceinline__ Ranges(int n_units, int nb, int nw, long long w_cap) : n_b(nb), n_w(nw), per_unit(nb + nw + 1) {
+        Cu = C::cv + (unsigned)nb * C::cb + (unsigned)nw * C::cw + C::cn;
+        Ctot = (unsigned long long)n_units * Cu;
+        constexpr unsigned cmax = C::cv + (C::cb > C::cw ? (C::cb > C::cn ? C::cb : C::cn) : (C::cw > C::cn ? C::cw : C::cn));
+        const unsigned long long n_items = (unsigned long long)n_units * per_unit;
+        unsigned long long w = (unsigned long long)w_cap;
+        w = w < Ctot / cmax ? w : Ctot / cmax;
+        w = w < n_items ? w : n_items;
+        W = (unsigned)(w < 1 ? 1 : w);
+        small = (Ctot + Cu) * W < (1ull << 32);
+    }
+    __host__ __device__ __forceinline__ unsigned kj(int j) const {                    // cost of items 0 .. j-1 of a unit
+        if (j <= 0) return 0u;
+        const int jb = min(j, n_b), jw = min(max(j - n_b, 0), n_w);
+        return C::cv + (unsigned)jb * C::cb + (unsigned)jw * C::cw + (j > n_b + n_w ? C::cn : 0u);
+    }
+    __host__ __device__ __forceinline__ int owner(int unit, int j) const {
+        if (small) return (int)(((unsigned)unit * Cu + kj(j)) * W / (unsigned)Ctot);
+        return (int)(((unsigned long long)unit * Cu + kj(j)) * W / Ctot);
+    }
+    __host__ __device__ __forceinline__ void lo(int w, int& unit, int& j) const {     // first position of range w (w == W: the end)
+        unsigned long long x;
+        if (small) x = ((unsigned)w * (unsigned)Ctot + W - 1u) / W;
+        else x = ((unsigned long long)w * Ctot + W - 1ull) / W;
+        unit = small ? (int)((unsigned)x / Cu) : (int)(x / Cu);
+        const unsigned rem = (unsigned)(x - (unsigned long long)unit * Cu);
+        if (rem == 0u) { j = 0; return; }
+        if (rem <= C::cv) j = 1;
+        else {
+            const unsigned r = rem - C::cv;
+            if (r <= (unsigned)n_b * C::cb) j = (int)((r + C::cb - 1u) / C::cb);
+            else if (r <= (unsigned)n_b * C::cb + (unsigned)n_w * C::cw) j = n_b + (int)((r - (unsigned)n_b * C::cb + C::cw - 1u) / C::cw);
+            else j = per_unit;
+        }
+        if (j >= per_unit) { j = 0; ++unit; }
     }
 };
 
@@ -638,15 +729,15 @@ qk_kernel(const AttnParams p)
     const int gw = blockIdx.x * kCW + warp;
     if (!sched_ok(s, c, p.max_kv_len)) { if (gw == 0 && lane == 0) c.state[6] = KIVI_STATE_ERR_CAPACITY; return; }
     KIVI_TL(0, gw, 0);
-    const long long N = (long long)p.n_units * s.ipu;                        // pseudo-blocks of the whole job
-    const long long W = min((long long)p.nw_eff, N);
-    if (gw >= W) return;
-    const Ranges rg(N, W);
-    const int lo = rg.lo(gw), hi = rg.lo(gw + 1);
+    const Ranges<CostQK> rg(p.n_units, s.n_kb, s.n_kr, p.nw_eff);           // items of the whole job over the range owners
+    if (gw >= (int)rg.W) return;
+    int u_lo, j_lo, u_hi, j_hi;
+    rg.lo(gw, u_lo, j_lo); rg.lo(gw + 1, u_hi, j_hi);
+    const int n_mine = (u_hi - u_lo) * s.ipu + (j_hi - j_lo);
     Pipe pp;
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
     Cursor cur;
-    cur.unit = lo / s.ipu; cur.j = lo - cur.unit * s.ipu; cur.half = 0; cur.left = hi - lo;
+    cur.unit = u_lo; cur.j = j_lo; cur.half = 0; cur.left = n_mine;
     for (int i = 0; i < p.spw; ++i) qk_issue_next<KB, GS>(pp, cur, p, s, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
@@ -654,7 +745,7 @@ qk_kernel(const AttnParams p)
     const int h_l = t4 % G;
     const bool slow = p.mask || p.dbg_logits;                                // mask / debug copies: rare, off the fast path
 
-    int unit = lo / s.ipu, j = lo - unit * s.ipu, left = hi - lo;
+    int unit = u_lo, j = j_lo, left = n_mine;
     // q of a unit, fetched one unit ahead (registers): lane = (chunk, t) of the B-fragment pairs / 4 channels of the fp32 copy
     uint2 qf[G], ql[G];
     auto fetch_q = [&](int un) {
@@ -810,7 +901,7 @@ qk_kernel(const AttnParams p)
         }
 
         // ---- this range's statistics of the unit, per head: slot = index of this warp among the unit's range owners
-        const int w_first = rg.owner(unit * s.ipu);
+        const int w_first = rg.owner(unit, 0);
         #pragma unroll
         for (int h = 0; h < G; ++h) {
             float m = -INFINITY, sm = 0.f;
@@ -912,33 +1003,32 @@ sv_kernel(const AttnParams p)
     const int gw = blockIdx.x * kCW + warp;
     if (!sched_ok(s, c, p.max_kv_len)) return;                               // the q.K^T kernel has flagged state[6]
     KIVI_TL(1, gw, 0);
-    const long long N = (long long)p.n_units * s.bpu;                       // pseudo-blocks of the whole job
-    const long long W = min((long long)p.nw_eff, N);                        // range owners: every range is non-empty
-    if (gw >= W) return;
-    const Ranges rg(N, W);
-    const int lo = rg.lo(gw), hi = rg.lo(gw + 1);
+    const Ranges<CostSV> rg(p.n_units, s.n_vb, s.n_vr, p.nw_eff);           // range owners: every range is non-empty
+    if (gw >= (int)rg.W) return;
+    int u_lo, j_lo, u_hi, j_hi;
+    rg.lo(gw, u_lo, j_lo); rg.lo(gw + 1, u_hi, j_hi);
+    const int n_mine = (u_hi - u_lo) * s.bpu + (j_hi - j_lo);
     const int ratio = c.H / c.Hkv;
     Pipe pp;
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
     Cursor cur;
-    cur.unit = lo / s.bpu; cur.j = lo - cur.unit * s.bpu; cur.half = 0; cur.left = hi - lo;
+    cur.unit = u_lo; cur.j = j_lo; cur.half = 0; cur.left = n_mine;
     pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
 
     constexpr int NG = Cols<G, GS>::NG;
     const int h_l = t4 % G;
     constexpr int kHalfBytes = kHalfChunks * Lay<VB>::kChunkBytes + kHalfChunks * NG * 64;   // codes + meta of half a V block
     const int rec = G * 2 * kD;                                              // floats of a partial record
-    const long long Nq = (long long)p.n_units * s.ipu;
-    const Ranges rq(Nq, min((long long)p.nw_eff, Nq));                      // the qk kernel's ranges
+    const Ranges<CostQK> rq(p.n_units, s.n_kb, s.n_kr, p.nw_eff);           // the qk kernel's ranges
 
-    int unit = lo / s.bpu, j = lo - unit * s.bpu, left = hi - lo;
+    int unit = u_lo, j = j_lo, left = n_mine;
     // statistics slots of a unit, fetched one unit ahead: lane i holds slot i of every head
     float2 sn[G];
     int nstat = 0;
     auto fetch_stats = [&](int un) {
         const int u_ = p.hchunks == 1 ? un : un / p.hchunks, hc_ = p.hchunks == 1 ? 0 : un % p.hchunks;
         const int row0 = u_ * ratio + hc_ * G;
-        nstat = rq.owner(un * s.ipu + s.ipu - 1) - rq.owner(un * s.ipu) + 1;
+        nstat = rq.owner(un, s.ipu - 1) - rq.owner(un, 0) + 1;
         #pragma unroll
         for (int h = 0; h < G; ++h) {
             sn[h] = make_float2(-INFINITY, 0.f);
@@ -1166,8 +1256,7 @@ sv_kernel(const AttnParams p)
         }
 
         // ---- this warp's partial record of the unit: [G][packed | window][128]
-        const int gb0 = unit * s.bpu;
-        const int w_first = rg.owner(gb0), w_last = rg.owner(gb0 + s.bpu - 1);
+        const int w_first = rg.owner(unit, 0), w_last = rg.owner(unit, s.bpu - 1);
         const int nparts = w_last - w_first + 1;
         float* recp = p.w.part + ((int64_t)unit * p.w.part_cap + (gw - w_first)) * rec;
         {

@@ -22,6 +22,11 @@
 
 namespace kivi {
 
+// kivi_bgemv_mma.cu: tensor-core path for the two hot shapes on the reference layout (KIVI_ERR_UNSUPPORTED = not eligible)
+int bgemv_ref_mma(const __half* A, long long a_stride, const uint32_t* qB, long long qb_us, long long qb_rs,
+                  const __half* S, const __half* Z, long long sz_us, long long sz_rs, __half* C,
+                  int B, int nh, int nh_kv, int K, int N, int bits, int g, cudaStream_t st);
+
 template <int BITS> struct CellWords;                       // 32 elements of BITS bits
 template <> struct CellWords<2> { using vec_t = uint2; static constexpr int kWords = 2; };
 template <> struct CellWords<4> { using vec_t = uint4; static constexpr int kWords = 4; };
@@ -377,6 +382,11 @@ static int launch_bgemv(const GemvArgs& a, int layout) {
         bgemv_kernel_layout_kernel<BITS><<<grid, 128, 0, a.st>>>(a.A, a.a_stride, a.qB, a.qb_us, a.qb_rs, a.S, a.Z,
                                                                   a.sz_us, a.sz_rs, a.C, ratio, a.K, a.N, a.g);
         return post_launch();
+    }
+    if (!tuning().no_mma_gemv) {
+        const int rc = bgemv_ref_mma(a.A, a.a_stride, a.qB, a.qb_us, a.qb_rs, a.S, a.Z, a.sz_us, a.sz_rs, a.C,
+                                     a.B, a.nh, a.nh_kv, a.K, a.N, BITS, a.g, a.st);
+        if (rc != KIVI_ERR_UNSUPPORTED) return rc;
     }
     constexpr int kCellBytes = 4 * BITS;                          // 32 elements
     const bool fast = (a.g % 32 == 0) &&

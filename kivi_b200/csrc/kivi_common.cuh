@@ -45,7 +45,7 @@ inline int ensure_dynamic_smem(F kernel, int bytes, int ordinal, std::atomic<uns
 
 // Tuning knobs from the environment, read ONCE per process (kivi_api.cu); 0 = not set.  Production callers never set
 // them (tools/microbench.py, tools/sweep_*.sh do).
-struct Tuning { int gqa_g, ctas_per_sm, stages_per_warp, no_pdl; };
+struct Tuning { int gqa_g, ctas_per_sm, stages_per_warp, no_pdl, no_mma_gemv; };
 const Tuning& tuning();
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -61,6 +61,22 @@ extern "C" int kivi_decode_attention_f16(const kivi_cache_t* cache, const void* 
     return KIVI_ERR_BITS;
 }
 
+// Test hook (tests/test_ranges_cpu.py): the work split of the decode kernels, evaluated on the host.  kernel 0 = q.K^T costs,
+// 1 = p.V costs; out_lo receives (unit, item) of the first position of ranges 0 .. W (2 * (W + 1) ints, the last = the end);
+// out_owner (may be NULL) receives owner(unit, item) for every position in order.  Returns W (or a negative error).
+extern "C" int kivi_debug_range_split(int n_units, int n_b, int n_w, int w_cap, int kernel, int* out_lo, int* out_owner)
+{
+    if (n_units <= 0 || n_b < 0 || n_w < 0 || w_cap <= 0 || !out_lo) return KIVI_ERR_SHAPE;
+    auto run = [&](auto rg) {
+        for (int w = 0; w <= (int)rg.W; ++w) rg.lo(w, out_lo[2 * w], out_lo[2 * w + 1]);
+        if (out_owner)
+            for (int u = 0; u < n_units; ++u)
+                for (int j = 0; j < rg.per_unit; ++j) out_owner[(long long)u * rg.per_unit + j] = rg.owner(u, j);
+        return (int)rg.W;
+    };
+    return kernel == 0 ? run(Ranges<CostQK>(n_units, n_b, n_w, w_cap)) : run(Ranges<CostSV>(n_units, n_b, n_w, w_cap));
+}
+
 #if KIVI_TIMELINE
 #include <vector>
 namespace kivi {

@@ -133,6 +133,8 @@ DECODE_CASES = [  # B, H, Hkv, kb, vb, g, R, n_prefill, steps
     (1, 8, 1, 4, 4, 64, 64, 130, 70),       # ratio 8 -> two chunks of 4, 4-bit g64
     (1, 2, 1, 2, 4, 32, 64, 10, 80),        # G = 2, mixed bits, starts below R (no packed part at first)
     (1, 3, 3, 4, 2, 128, 128, 0, 135),      # decode from an EMPTY cache, g = 128
+    (1, 2, 1, 4, 2, 64, 256, 250, 20),      # R = 256: a K flush fills two 128-token blocks (step 6)
+    (2, 2, 2, 2, 2, 128, 256, 250, 20),     # R = 256, g = 128, 2-bit: flush at step 6 into blocks 0 and 1
 ]
 
 

@@ -50,3 +50,34 @@ for kname, kk, cols in (("qk", 0, (0, 1, 3)), ("sv", 1, (0, 1, 2, 3))):
         print(f"   {names[c]:22s} min {x.min():7.2f}  p10 {np.percentile(x, 10):7.2f}  median {np.median(x):7.2f}  p90 {np.percentile(x, 90):7.2f}  max {x.max():7.2f} us")
     d = rel[:, cols[-1]] - rel[:, 0]
     print(f"   warp lifetime          min {d.min():7.2f}  median {np.median(d):7.2f}  max {d.max():7.2f} us")
+
+# ---- cost regression: warp lifetime against the composition of its range (the split the library itself computes)
+def _composition(kernel, n_units, n_b, n_w, w_cap):
+    fn = _lib.bind("kivi_debug_range_split", ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p])
+    per_unit = n_b + n_w + 1
+    lo = np.zeros((w_cap + 2, 2), np.int32)
+    owner = np.zeros(n_units * per_unit, np.int32)
+    W = fn(n_units, n_b, n_w, w_cap, kernel, lo.ctypes.data, owner.ctypes.data)
+    j = np.tile(np.arange(per_unit), n_units)
+    unit = np.repeat(np.arange(n_units), per_unit)
+    nb = np.bincount(owner, weights=(j < n_b), minlength=W)
+    nw = np.bincount(owner, weights=((j >= n_b) & (j < n_b + n_w)), minlength=W)
+    nn = np.bincount(owner, weights=(j == per_unit - 1), minlength=W)
+    visits = np.array([len(np.unique(unit[owner == w])) for w in range(W)], float)
+    return W, np.c_[nb, nw, nn, visits]
+
+
+R = cache.residual_length
+n_units = B * Hkv
+w_cap = int(act.sum())
+for kname, kk, (n_b, n_w), c0 in (("qk", 0, (cache.tk // 128, -(-cache.r // 16)), 0), ("sv", 1, (-(-cache.tv // 128), -(-cache.L // 16)), 1)):
+    W, X = _composition(kk, n_units, n_b, n_w, w_cap)
+    a = buf[kk]
+    life = (a[:W, 3].astype(np.float64) - a[:W, c0].astype(np.float64)) / 1e3
+    # items sum to ~const per warp: regress on (window items, new tokens, visits) with blocks absorbed by "per item"
+    A = np.c_[X.sum(1) - X[:, 3], X[:, 1], X[:, 2], X[:, 3]]          # [items, of which window, of which new, visits]
+    coef, *_ = np.linalg.lstsq(A, life, rcond=None)
+    blk = coef[0]
+    print(f"{kname}: {W} ranges, items/range {A[:, 0].min():.0f}..{A[:, 0].max():.0f}; lifetime = {blk:.3f} us/block, window item "
+          f"{(blk + coef[1]) / blk:.2f} blocks, new token {(blk + coef[2]) / blk:.2f}, visit {coef[3] / blk:.2f}; "
+          f"residual std {np.std(life - A @ coef):.2f} us, lifetime std {life.std():.2f} us, max - median {life.max() - np.median(life):.2f} us")
