@@ -444,118 +444,106 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
         }
         __syncwarp();
     }
-    // ---- K: k_new joins the window, or completes it -> quantise the R tokens per channel
+    // ---- K: k_new joins the window.  (When it COMPLETES the window, r + 1 == R, the whole window is quantised instead:
+    // k_flush_slice below, spread over all warps of the p.V kernel.)
     if (s.r + 1 < c.R) {
         if (lane >= 16) reinterpret_cast<uint4*>(c.k_res + (int64_t)u * c.R * kD)[win_unit(s.r, lane - 16)] = knew4;
-    } else {
-        // once per R steps.  lane = (hw, cu): token parity hw = lane >> 4, channels 8 cu .. 8 cu + 7 (cu = lane & 15): every
-        // window row is read with 128-bit loads (a lane's 16-byte unit of the swizzled row), twice per group (min / max, then
-        // codes).  A lane then owns whole 32-bit words of the destination block -- the channel pairs (8 cu + 2q, + 1), the
-        // rows 2m + hw of a slab, all their fields -- assembled in registers and stored once per slab.
-        constexpr int F = 16 / KB, kSlabRows = 16 * F, kSlabs = 128 / kSlabRows;
-        const float maxq = (float)((1 << KB) - 1);
-        const int bb = lay_block_bytes(KB, g);
-        uint8_t* ub = c.k_store + (int64_t)u * c.k_cap_blocks * bb;
-        const __half* win = c.k_res + (int64_t)u * c.R * kD;
-        const __half* knew = p.k_new + (int64_t)u * kD;
-        const int nblk = max(1, c.R / kBlockTokens);                                    // R in {32, 64, 128, 256}
-        const int cnt = min(c.R, kBlockTokens);                                         // flushed tokens per destination block
-        const int hw = lane >> 4, cu = lane & 15;
-        auto row8 = [&](int t) -> uint4 {                                               // window token t, channels 8 cu .. + 7
-            return t < c.R - 1 ? __ldcg(reinterpret_cast<const uint4*>(win + (int64_t)t * kD) + (cu ^ (t & 7)))
-                               : __ldg(reinterpret_cast<const uint4*>(knew) + cu);
-        };
-        // word (q, m) of slab sl: inner pair 8 cu + 2q (+1), row 2m + hw  (kivi_decode.cuh: lane' = (row & 7) * 4 + q, r = 2 (cu & 1) + (row >> 3))
-        auto word_ptr = [&](uint8_t* blk, int sl, int q, int m) -> uint32_t* {
-            const int row = 2 * m + hw;
-            return reinterpret_cast<uint32_t*>(blk) + (((cu >> 1) * kSlabs + sl) * 128 + ((row & 7) * 4 + q) * 4 + (cu & 1) * 2 + (row >> 3));
-        };
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K flush (models/llama_kivi.py:343-356), once per R steps: the R window tokens (R - 1 rows of the fp16 window + k_new) of
+// a unit are quantised per channel in groups of g tokens, straight into the fragment words of the K store.  It depends on
+// nothing the attention computes and touches nothing the attention reads (blocks past tk, meta of new groups), so the
+// p.V kernel does it up front, while it would otherwise wait for the q.K^T kernel to drain, spread over ALL its warps:
+// slice (unit, q) = the channel pairs (8 cu + 2q, + 1), cu = 0..15, of one unit.  lane = (hw, cu): token parity hw = lane >> 4.
+// A lane owns whole 32-bit words of the destination block (its channel pair, rows 2m + hw of a slab, all their fields):
+// assembled in registers, stored once per slab, read-modify-write only when R < 128 leaves other tokens' fields in the word.
+// (Done by the last-arriving warp of each unit at the tail of its range, the flush cost 3.8 ms per flush step at cfg 2.)
+// ------------------------------------------------------------------------------------------------
+template <int KB>
+__device__ __noinline__ void k_flush_slice(const AttnParams& p, const Sched& s, int u, int q, int lane)
+{
+    const CacheDesc& c = p.c;
+    const int g = c.g;
+    constexpr int F = 16 / KB, kSlabRows = 16 * F, kSlabs = 128 / kSlabRows;
+    const float maxq = (float)((1 << KB) - 1);
+    const int bb = lay_block_bytes(KB, g);
+    uint8_t* ub = c.k_store + (int64_t)u * c.k_cap_blocks * bb;
+    const __half* win = c.k_res + (int64_t)u * c.R * kD;
+    const __half* knew = p.k_new + (int64_t)u * kD;
+    const int nblk = max(1, c.R / kBlockTokens);                                        // R in {32, 64, 128, 256}
+    const int cnt = min(c.R, kBlockTokens);                                             // flushed tokens per destination block
+    const int hw = lane >> 4, cu = lane & 15;
+    auto row2 = [&](int t) -> __half2 {                                                 // window token t, channels 8 cu + 2q, + 1
+        return t < c.R - 1 ? u32_as_h2(__ldcg(reinterpret_cast<const uint32_t*>(win + (int64_t)t * kD + ((cu ^ (t & 7)) << 3)) + q))
+                           : u32_as_h2(__ldg(reinterpret_cast<const uint32_t*>(knew + 8 * cu) + q));
+    };
+    #pragma unroll 1
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int tb = s.tk + bi * kBlockTokens;                                        // first flushed token of this block
+        const int o0 = tb % kBlockTokens;                                               // its outer index (multiple of R)
+        uint8_t* blk = ub + (int64_t)(tb / kBlockTokens) * bb;
+        const bool partial = cnt < kBlockTokens;                                        // other fields of the words are live data
+        // word m of slab sl: inner pair 8 cu + 2q (+1), row 2m + hw   (kivi_decode.cuh: lane' = (row & 7) * 4 + q, r = 2 (cu & 1) + (row >> 3))
+        uint32_t* wbase = reinterpret_cast<uint32_t*>(blk) + (cu >> 1) * kSlabs * 128 + (cu & 1) * 2 + q * 4;
+        uint32_t words[8];
+        int cur_sl = -1;
         #pragma unroll 1
-        for (int bi = 0; bi < nblk; ++bi) {
-            const int tb = s.tk + bi * kBlockTokens;                                    // first flushed token of this block
-            const int o0 = tb % kBlockTokens;                                           // its outer index (multiple of R)
-            uint8_t* blk = ub + (int64_t)(tb / kBlockTokens) * bb;
-            const bool partial = cnt < kBlockTokens;                                    // other fields of the words are live data
-            uint32_t words[4][8];
-            int cur_sl = -1;
-            auto store_slab = [&]() {
-                #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    #pragma unroll
-                    for (int m = 0; m < 8; ++m) *word_ptr(blk, cur_sl, q, m) = words[q][m];
-            };
+        for (int gl = 0; gl < cnt / g; ++gl) {                                          // groups landing in this block
+            const int tl0 = bi * kBlockTokens + gl * g;                                 // first token of the group within the window
+            float mn0 = INFINITY, mx0 = -INFINITY, mn1 = INFINITY, mx1 = -INFINITY;
             #pragma unroll 1
-            for (int gl = 0; gl < cnt / g; ++gl) {                                      // groups landing in this block
-                const int tl0 = bi * kBlockTokens + gl * g;                             // first token of the group within the window
-                float mnf[8], mxf[8];
+            for (int i0 = 0; i0 < g; i0 += 16) {                                        // 8 rows of this parity per pass (independent loads)
+                __half2 v[8];
                 #pragma unroll
-                for (int e = 0; e < 8; ++e) { mnf[e] = INFINITY; mxf[e] = -INFINITY; }
-                #pragma unroll 1
-                for (int i0 = 0; i0 < g; i0 += 16) {                                    // 8 rows of this parity per pass (independent loads)
-                    uint4 v[8];
-                    #pragma unroll
-                    for (int m = 0; m < 8; ++m) v[m] = row8(tl0 + i0 + 2 * m + hw);
-                    #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const __half2* h2 = reinterpret_cast<const __half2*>(&v[m]);
-                        #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 f = __half22float2(h2[q]);
-                            mnf[2 * q] = fminf(mnf[2 * q], f.x); mxf[2 * q] = fmaxf(mxf[2 * q], f.x);
-                            mnf[2 * q + 1] = fminf(mnf[2 * q + 1], f.y); mxf[2 * q + 1] = fmaxf(mxf[2 * q + 1], f.y);
-                        }
-                    }
-                }
-                float scf[8];
-                const int og = o0 + gl * g;                                             // outer index of the group's first token
-                __half sc16[8], mn16[8];
+                for (int m = 0; m < 8; ++m) v[m] = row2(tl0 + i0 + 2 * m + hw);
                 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    mnf[e] = fminf(mnf[e], __shfl_xor_sync(0xffffffffu, mnf[e], 16));   // the other token parity
-                    mxf[e] = fmaxf(mxf[e], __shfl_xor_sync(0xffffffffu, mxf[e], 16));
-                    const __half d16 = __float2half_rn(mxf[e] - mnf[e]);
-                    sc16[e] = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
-                    scf[e] = __half2float(sc16[e]);
-                    mn16[e] = __float2half_rn(mnf[e]);
-                }
-                if (hw == 0) {
-                    // meta entry of (chunk cu >> 1, group og / g, t = q): { z[2q], z[2q+1], s[2q], s[2q+1] } of the lane's half (cu & 1)
-                    #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        __align__(8) __half mz[4] = {mn16[2 * q], mn16[2 * q + 1], sc16[2 * q], sc16[2 * q + 1]};
-                        *reinterpret_cast<uint2*>(blk + lay_zero_off(KB, g, 8 * cu + 2 * q, og / g)) = *reinterpret_cast<const uint2*>(mz);
-                    }
-                }
-                #pragma unroll 1
-                for (int q16 = 0; q16 < g / 16; ++q16) {
-                    const int o = og + 16 * q16;                                        // outer index of row 0 of this 16-token chunk
-                    const int sl = o / kSlabRows, j = (o % kSlabRows) / 16;
-                    if (sl != cur_sl) {
-                        if (cur_sl >= 0) store_slab();
-                        cur_sl = sl;
-                        #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            #pragma unroll
-                            for (int m = 0; m < 8; ++m) words[q][m] = partial ? *word_ptr(blk, sl, q, m) : 0u;
-                    }
-                    uint4 v[8];
-                    #pragma unroll
-                    for (int m = 0; m < 8; ++m) v[m] = row8(tl0 + 16 * q16 + 2 * m + hw);
-                    const uint32_t keep = ~((((1u << KB) - 1u) * 0x00010001u) << (KB * j));
-                    #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const __half2* h2 = reinterpret_cast<const __half2*>(&v[m]);
-                        #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 f = __half22float2(h2[q]);
-                            const uint32_t c0 = (uint32_t)__float2int_rn(q_code(f.x, mnf[2 * q], scf[2 * q], maxq));
-                            const uint32_t c1 = (uint32_t)__float2int_rn(q_code(f.y, mnf[2 * q + 1], scf[2 * q + 1], maxq));
-                            words[q][m] = (words[q][m] & keep) | ((c0 | (c1 << 16)) << (KB * j));
-                        }
-                    }
+                for (int m = 0; m < 8; ++m) {
+                    const float2 f = __half22float2(v[m]);
+                    mn0 = fminf(mn0, f.x); mx0 = fmaxf(mx0, f.x);
+                    mn1 = fminf(mn1, f.y); mx1 = fmaxf(mx1, f.y);
                 }
             }
-            if (cur_sl >= 0) store_slab();
+            mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, 16)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 16));   // the other token parity
+            mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, 16)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 16));
+            const __half sc0 = __float2half_rn(__fdiv_rn(__half2float(__float2half_rn(mx0 - mn0)), maxq));
+            const __half sc1 = __float2half_rn(__fdiv_rn(__half2float(__float2half_rn(mx1 - mn1)), maxq));
+            const float scf0 = __half2float(sc0), scf1 = __half2float(sc1);
+            const int og = o0 + gl * g;                                                 // outer index of the group's first token
+            if (hw == 0) {                                                              // meta entry half: { z, z', s, s' } of the pair
+                __align__(8) __half mz[4] = {__float2half_rn(mn0), __float2half_rn(mn1), sc0, sc1};
+                *reinterpret_cast<uint2*>(blk + lay_zero_off(KB, g, 8 * cu + 2 * q, og / g)) = *reinterpret_cast<const uint2*>(mz);
+            }
+            #pragma unroll 1
+            for (int q16 = 0; q16 < g / 16; ++q16) {
+                const int o = og + 16 * q16;                                            // outer index of row 0 of this 16-token chunk
+                const int sl = o / kSlabRows, j = (o % kSlabRows) / 16;
+                if (sl != cur_sl) {
+                    if (cur_sl >= 0) {
+                        #pragma unroll
+                        for (int m = 0; m < 8; ++m) wbase[cur_sl * 128 + ((2 * m + hw) & 7) * 16 + ((2 * m + hw) >> 3)] = words[m];
+                    }
+                    cur_sl = sl;
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) words[m] = partial ? wbase[sl * 128 + ((2 * m + hw) & 7) * 16 + ((2 * m + hw) >> 3)] : 0u;
+                }
+                const uint32_t keep = ~((((1u << KB) - 1u) * 0x00010001u) << (KB * j));
+                __half2 v[8];
+                #pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = row2(tl0 + 16 * q16 + 2 * m + hw);
+                #pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float2 f = __half22float2(v[m]);
+                    const uint32_t c0 = (uint32_t)__float2int_rn(q_code(f.x, mn0, scf0, maxq));
+                    const uint32_t c1 = (uint32_t)__float2int_rn(q_code(f.y, mn1, scf1, maxq));
+                    words[m] = (words[m] & keep) | ((c0 | (c1 << 16)) << (KB * j));
+                }
+            }
+        }
+        if (cur_sl >= 0) {
+            #pragma unroll
+            for (int m = 0; m < 8; ++m) wbase[cur_sl * 128 + ((2 * m + hw) & 7) * 16 + ((2 * m + hw) >> 3)] = words[m];
         }
     }
 }
@@ -605,8 +593,11 @@ struct CostSV { static constexpr unsigned cb = KIVI_UNIFORM_RANGES ? 1 : 16, cw 
 template <class C>
 struct Ranges {
     int n_b, n_w, per_unit;
-    unsigned Cu, W; unsigned long long Ctot; bool small;
-    __host__ __device__ __forceinline__ Ranges(int n_units, int nb, int nw, long long w_cap) : n_b(nb), n_w(nw), per_unit(nb + nw + 1) {
+    unsigned Cu, W; unsigned long long Ctot; int small;
+    // a plain struct: the kernels keep ONE copy per CTA in shared memory (its ~8 words would otherwise stay live in registers
+    // across the block loops; they are read once per (warp, unit) visit)
+    __host__ __device__ __forceinline__ void init(int n_units, int nb, int nw, long long w_cap) {
+        n_b = nb; n_w = nw; per_unit = nb + nw + 1;
         Cu = C::cv + (unsigned)nb * C::cb + (unsigned)nw * C::cw + C::cn;
         Ctot = (unsigned long long)n_units * Cu;
         constexpr unsigned cmax = C::cv + (C::cb > C::cw ? (C::cb > C::cn ? C::cb : C::cn) : (C::cw > C::cn ? C::cw : C::cn));
@@ -615,7 +606,7 @@ struct Ranges {
         w = w < Ctot / cmax ? w : Ctot / cmax;
         w = w < n_items ? w : n_items;
         W = (unsigned)(w < 1 ? 1 : w);
-        small = (Ctot + Cu) * W < (1ull << 32);
+        small = (Ctot + Cu) * W < (1ull << 32) ? 1 : 0;
     }
     __host__ __device__ __forceinline__ unsigned kj(int j) const {                    // cost of items 0 .. j-1 of a unit
         if (j <= 0) return 0u;
@@ -717,20 +708,24 @@ qk_kernel(const AttnParams p)
     uint2* q2 = reinterpret_cast<uint2*>(ptr) + warp * (G * 32);             // per warp: [G][8 chunks][4 t] half2 pairs
     float* qlin = reinterpret_cast<float*>(ptr + kCW * G * 32 * 8) + warp * (G * kD);   // per warp: [G][128] fp32
 
+    __shared__ Ranges<CostQK> rg_sh;                                         // items of the whole job over the range owners
+    const Sched s = make_sched(c);
     if (tid == 0) {
         for (int i = 0; i < n_stages; ++i) mbar_init(&full_all[i], 1);
         mbar_fence_init();
+        rg_sh.init(p.n_units, s.n_kb, s.n_kr, p.nw_eff);
     }
-    __syncthreads();                                                         // the only CTA barrier: mbarrier init
+    __syncthreads();                                                         // the only CTA barrier: mbarrier init, work split
     pdl_trigger();                                                           // the p.V kernel may start its prologue
 
-    const Sched s = make_sched(c);
     const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
     if (!sched_ok(s, c, p.max_kv_len)) { if (gw == 0 && lane == 0) c.state[6] = KIVI_STATE_ERR_CAPACITY; return; }
     KIVI_TL(0, gw, 0);
-    const Ranges<CostQK> rg(p.n_units, s.n_kb, s.n_kr, p.nw_eff);           // items of the whole job over the range owners
-    if (gw >= (int)rg.W) return;
+    const Ranges<CostQK>& rg = rg_sh;
+    // a warp without a range still waits for the predecessor grid: a CTA leaves (and hands its SM to a p.V CTA, which reads
+    // k_new for the K flush before its own wait) only when the kernel that produced q / k_new / v_new has completed
+    if (gw >= (int)rg.W) { pdl_wait(); return; }
     int u_lo, j_lo, u_hi, j_hi;
     rg.lo(gw, u_lo, j_lo); rg.lo(gw + 1, u_hi, j_hi);
     const int n_mine = (u_hi - u_lo) * s.ipu + (j_hi - j_lo);
@@ -992,18 +987,22 @@ sv_kernel(const AttnParams p)
     float* obuf = reinterpret_cast<float*>(ptr) + warp * (G * kD);             // per warp: [G][128] window-item outputs in channel order
     uint8_t* scratch = reinterpret_cast<uint8_t*>(obuf);                     // commit_unit scratch (128 bytes), same storage
 
+    __shared__ Ranges<CostSV> rg_sh;                                         // this kernel's work split
+    __shared__ Ranges<CostQK> rq_sh;                                         // the q.K^T kernel's (statistics slots per unit)
+    const Sched s = make_sched(c);
     if (tid == 0) {
         for (int i = 0; i < n_stages; ++i) mbar_init(&full_all[i], 1);
         mbar_fence_init();
+        rg_sh.init(p.n_units, s.n_vb, s.n_vr, p.nw_eff);
+        rq_sh.init(p.n_units, s.n_kb, s.n_kr, p.nw_eff);
     }
-    __syncthreads();                                                         // the only CTA barrier: mbarrier init
+    __syncthreads();                                                         // the only CTA barrier: mbarrier init, work splits
 
-    const Sched s = make_sched(c);
     const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
     const int gw = blockIdx.x * kCW + warp;
     if (!sched_ok(s, c, p.max_kv_len)) return;                               // the q.K^T kernel has flagged state[6]
     KIVI_TL(1, gw, 0);
-    const Ranges<CostSV> rg(p.n_units, s.n_vb, s.n_vr, p.nw_eff);           // range owners: every range is non-empty
+    const Ranges<CostSV>& rg = rg_sh;                                        // range owners: every range is non-empty
     if (gw >= (int)rg.W) return;
     int u_lo, j_lo, u_hi, j_hi;
     rg.lo(gw, u_lo, j_lo); rg.lo(gw + 1, u_hi, j_hi);
@@ -1013,13 +1012,17 @@ sv_kernel(const AttnParams p)
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
     Cursor cur;
     cur.unit = u_lo; cur.j = j_lo; cur.half = 0; cur.left = n_mine;
+    if (s.r + 1 == c.R) {                                                    // the step that completes the K window: flush it now
+        const int n_slices = 4 * c.B * c.Hkv, n_workers = (int)rg.W;
+        for (int sl = gw; sl < n_slices; sl += n_workers) k_flush_slice<KB>(p, s, sl >> 2, sl & 3, lane);
+    }
     pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
 
     constexpr int NG = Cols<G, GS>::NG;
     const int h_l = t4 % G;
     constexpr int kHalfBytes = kHalfChunks * Lay<VB>::kChunkBytes + kHalfChunks * NG * 64;   // codes + meta of half a V block
     const int rec = G * 2 * kD;                                              // floats of a partial record
-    const Ranges<CostQK> rq(p.n_units, s.n_kb, s.n_kr, p.nw_eff);           // the qk kernel's ranges
+    const Ranges<CostQK>& rq = rq_sh;                                        // the qk kernel's ranges
 
     int unit = u_lo, j = j_lo, left = n_mine;
     // statistics slots of a unit, fetched one unit ahead: lane i holds slot i of every head
@@ -1331,7 +1334,7 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     int rc = device_info(&di);
     if (rc) return rc;
     const Tuning& tn = tuning();
-    const int max_smem = di.max_smem_optin;
+    const int max_smem = di.max_smem_optin - 1024;                           // room for the kernels' static shared memory (work split, 128 B)
     const int half_k = kHalfChunks * Lay<KB>::kChunkBytes + lay_meta_bytes(c.g) / kParts;
     const int half_v = kHalfChunks * Lay<VB>::kChunkBytes + lay_meta_bytes(c.g) / kParts + G * kPartTokens * 2;
     const int stage = max(max(half_k, half_v), kResBytes);
@@ -1340,13 +1343,13 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     int ctas = kMaxCtasPerSm;                                                // the kernels' __launch_bounds__
     p.spw = 0;
     for (; ctas >= 1; --ctas) {                                              // most CTAs per SM that still get >= 2 stages per warp
-        p.spw = min(4, (max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
+        p.spw = min(4, (max_smem / ctas - fixed) / (kCW * p.stage_bytes));
         if (p.spw >= 2) break;
     }
     if (ctas < 1) { ctas = 1; p.spw = (max_smem - fixed) / (kCW * p.stage_bytes); }
     if (tn.ctas_per_sm >= 1 && tn.ctas_per_sm <= ctas) {                     // tuning knobs (tools/microbench.py), read once per process
         ctas = tn.ctas_per_sm;
-        p.spw = min(8, (max_smem / ctas - 1024 - fixed) / (kCW * p.stage_bytes));
+        p.spw = min(8, (max_smem / ctas - fixed) / (kCW * p.stage_bytes));
     }
     if (tn.stages_per_warp >= 1 && tn.stages_per_warp <= p.spw) p.spw = tn.stages_per_warp;
     if (p.spw < 1) return KIVI_ERR_CAPACITY;

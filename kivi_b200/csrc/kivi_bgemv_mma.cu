@@ -132,7 +132,7 @@ struct Args {
 };
 
 // ------------------------------------------------------------------------------------------------
-// wide: K = 128 inner rows, N tokens.  grid = (U_kv, Y, ratio / G), block = 128 (4 warps).  The CTA streams 512-token tiles
+// wide: K = 128 inner rows, N tokens.  grid = (U_kv * ratio / G, Y), block = 128 (4 warps).  The CTA streams 512-token tiles
 // (full 128-byte line segments of every code row, one 32-byte sector of every scale / zero row) through two shared stages;
 // warp w contracts tokens 128 w .. 128 w + 127 of the tile.  16-byte units of a code row are XOR-swizzled with
 // 2 * (row & 3): the four t-lanes of a fragment load (rows r, r+1, r+2, r+3 of one word column) hit different bank octets.
@@ -164,7 +164,8 @@ wide_kernel(const Args a)
     float* xsc = qlin + G * 128;                                             // [G] 1 / prescale
     uint8_t* stage0 = smem + G * 768 + 64;
 
-    const int ukv = blockIdx.x, h0 = blockIdx.z * G;
+    const int zdim = a.ratio / G;                                           // head chunks of a unit sit in NEIGHBOURING CTAs: the second reader hits L2
+    const int ukv = blockIdx.x / zdim, h0 = (blockIdx.x % zdim) * G;
     // ---- x rows of the G heads: prescale, the fragment pairs and an fp32 copy (zero term)
     if (warp < G) {
         const __half* ap = a.A + ((long long)ukv * a.ratio + h0 + warp) * a.a_stride;
@@ -308,7 +309,7 @@ wide_kernel(const Args a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// tall: N = 128 outer, K tokens (inner).  grid = (U_kv, S, ratio / G) with cluster (1, S, 1); block = 256 (8 warps); the
+// tall: N = 128 outer, K tokens (inner).  grid = (U_kv * ratio / G, S) with cluster (1, S, 1); block = 256 (8 warps); the
 // 8 S warps of a cluster take the 128-token tiles of the unit round-robin.
 // ------------------------------------------------------------------------------------------------
 template <int BITS, int G, int GS>
@@ -328,7 +329,8 @@ tall_kernel(const Args a)
     uint8_t* wbase = smem + G * 512 + 256 + (size_t)warp * (2 * GE::kStage + 2 * G * 256);
     __half* xbuf = reinterpret_cast<__half*>(wbase + 2 * GE::kStage);        // [2 stages][G][128] prescaled x of the tile
 
-    const int ukv = blockIdx.x, h0 = blockIdx.z * G;
+    const int zdim = a.ratio / G;
+    const int ukv = blockIdx.x / zdim, h0 = (blockIdx.x % zdim) * G;
     const __half* arow = a.A + ((long long)ukv * a.ratio + h0) * a.a_stride;
     // ---- prescale per head: max |x| over the whole row (every CTA of the cluster computes the same value)
     {
@@ -521,7 +523,7 @@ static int launch_wide(const Args& a, int U, cudaStream_t st)
     const long long slots = (long long)di.num_sms * 4;
     int Y = (int)min((long long)n_tiles, max(1ll, (3 * slots + (long long)U * Z - 1) / ((long long)U * Z)));
     if (Y > 65535) Y = 65535;
-    wide_kernel<BITS, G, GS><<<dim3(U, Y, Z), 128, smem, st>>>(a);
+    wide_kernel<BITS, G, GS><<<dim3(U * Z, Y, 1), 128, smem, st>>>(a);
     return post_launch();
 }
 
@@ -541,7 +543,7 @@ static int launch_tall(const Args& a, int U, cudaStream_t st)
     int S = 1;                                                               // cluster size: split the tokens while the grid is short of 2 CTAs per SM
     while (S < 8 && (long long)U * Z * S < 2ll * di.num_sms && n_tiles >= 16 * S) S *= 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(U, S, Z); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(U * Z, S, 1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = S; attr[0].val.clusterDim.z = 1;
@@ -562,7 +564,7 @@ int bgemv_ref_mma(const __half* A, long long a_stride, const uint32_t* qB, long 
     if (!(bits == 2 || bits == 4) || !(g == 32 || g == 64)) return KIVI_ERR_UNSUPPORTED;
     const int ratio = nh / nh_kv, fpi = 32 / bits, NG = 128 / g;
     const long long U = (long long)B * nh_kv;
-    if (U > 0x7fffffff || ratio > 65535) return KIVI_ERR_UNSUPPORTED;
+    if (U * ratio > 0x7fffffff) return KIVI_ERR_UNSUPPORTED;
     int G = 1;                                                               // heads per CTA: (128 / g) * G <= 4 column pairs
     if (NG == 2 && ratio % 2 == 0) G = 2;
     bgm::Args a{A, a_stride, qB, qb_us, qb_rs, S, Z, sz_us, sz_rs, C, ratio, K, N, 0};
@@ -586,6 +588,10 @@ int bgemv_ref_mma(const __half* A, long long a_stride, const uint32_t* qB, long 
     }
     if (wide) {
         if (N % 64 != 0) return KIVI_ERR_UNSUPPORTED;                       // 16-byte code units must not straddle a row end mid-word pair
+        // Measured (tools/microbench.py, profiles/r02_microbench*.json): on THIS layout the merge (PRMT) and the scattered
+        // scale loads eat most of what the MMA saves; with one query head per KV head the SIMT kernel (one LOP3 + one FFMA per
+        // code on two different pipes) is 25 % faster, with shared KV heads (one FFMA per code AND head) the MMA kernel wins.
+        if (ratio < 2 || ratio / G > 2) return KIVI_ERR_UNSUPPORTED;
         KIVI_MMA_DISPATCH(launch_wide)
     }
     #undef KIVI_MMA_DISPATCH

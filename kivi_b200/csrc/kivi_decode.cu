@@ -74,7 +74,9 @@ extern "C" int kivi_debug_range_split(int n_units, int n_b, int n_w, int w_cap, 
                 for (int j = 0; j < rg.per_unit; ++j) out_owner[(long long)u * rg.per_unit + j] = rg.owner(u, j);
         return (int)rg.W;
     };
-    return kernel == 0 ? run(Ranges<CostQK>(n_units, n_b, n_w, w_cap)) : run(Ranges<CostSV>(n_units, n_b, n_w, w_cap));
+    if (kernel == 0) { Ranges<CostQK> rg; rg.init(n_units, n_b, n_w, w_cap); return run(rg); }
+    Ranges<CostSV> rg; rg.init(n_units, n_b, n_w, w_cap);
+    return run(rg);
 }
 
 #if KIVI_TIMELINE

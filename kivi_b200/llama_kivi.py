@@ -268,6 +268,41 @@ class LlamaModel_KIVI(nn.Module):
         self.norm = LlamaRMSNorm(config.hidden_size, config.rms_norm_eps)
 
 
+class KiviPast(tuple):
+    """The per-layer `past_key_value` that forward() hands out while the cache lives in the pre-allocated KiviCache.
+    It indexes like the reference's 9-tuple (models/llama_kivi.py:454-455): [8] / [-1] is kv_seq_len (what
+    prepare_inputs_for_generation reads, :917) and costs nothing; the eight tensors are exported from the blocked cache
+    on first access (a snapshot).  Passing it back to forward() continues on the fused path; it is valid for that as long
+    as the cache has not moved on (one step per forward call, like the reference's functional tuples)."""
+
+    def __new__(cls, cache, layer: int, kv_len: int):
+        self = super().__new__(cls, ())
+        self.cache, self.layer, self.kv_len, self._fields = cache, layer, kv_len, None
+        return self
+
+    def materialise(self):
+        if self._fields is None:
+            if self.cache.kv_len != self.kv_len:
+                raise RuntimeError(f"stale KIVI cache view: it describes {self.kv_len} tokens, the cache now holds "
+                                   f"{self.cache.kv_len} (export a view before decoding further if you need a snapshot)")
+            self._fields = self.cache.export(self.layer)
+        return self._fields
+
+    def __len__(self):
+        return 9
+
+    def __getitem__(self, i):
+        if isinstance(i, int) and i in (8, -1):
+            return self.kv_len
+        return self.materialise()[i]
+
+    def __iter__(self):
+        return iter(self.materialise())
+
+    def __repr__(self):
+        return f"KiviPast(layer={self.layer}, kv_seq_len={self.kv_len})"
+
+
 class _Output(tuple):
     """What forward() returns when no transformers ModelOutput class is wanted: a (logits, past_key_values) tuple that
     also answers to the attribute names of CausalLMOutputWithPast."""
@@ -403,21 +438,72 @@ class LlamaForCausalLM_KIVI(nn.Module):
         if past_key_values is not None and len(past_key_values) == 0:
             past_key_values = None
         start = 0 if past_key_values is None else past_key_values[0][-1]
-        if position_ids is None:
-            position_ids = torch.arange(start, start + q_len, device=input_ids.device).unsqueeze(0).expand(B, -1)
-        rows = self._tables(input_ids.device)[0].shape[0]
-        if start + q_len > rows:            # the slow path's index_select would raise; say why
-            raise ValueError(f"{start + q_len} positions exceed config.max_position_embeddings = {rows}")
-        dtype = self.lm_head.weight.dtype
-        mask = _additive_mask(attention_mask, q_len, start + q_len, dtype, input_ids.device)
-        h, pasts = self._run_layers(input_ids, position_ids, past_key_values, mask)
-        logits = self.lm_head(h).float()                                     # logits.float() (:881)
+        fused = self._fused_forward_ok(input_ids, past_key_values, attention_mask, position_ids, start)
+        if fused:
+            logits, pasts = self._forward_fused(input_ids, past_key_values, start)
+        else:
+            if past_key_values is not None and isinstance(past_key_values[0], KiviPast):
+                past_key_values = [tuple(p.materialise()) for p in past_key_values]     # leave the fused path: plain 9-tuples
+            if position_ids is None:
+                position_ids = torch.arange(start, start + q_len, device=input_ids.device).unsqueeze(0).expand(B, -1)
+            rows = self._tables(input_ids.device)[0].shape[0]
+            if start + q_len > rows:            # the slow path's index_select would raise; say why
+                raise ValueError(f"{start + q_len} positions exceed config.max_position_embeddings = {rows}")
+            dtype = self.lm_head.weight.dtype
+            mask = _additive_mask(attention_mask, q_len, start + q_len, dtype, input_ids.device)
+            h, pasts = self._run_layers(input_ids, position_ids, past_key_values, mask)
+            logits = self.lm_head(h).float()                                     # logits.float() (:881)
         if return_dict is None:
             return_dict = getattr(self.config, "use_return_dict", False)
         if return_dict:
             from transformers.modeling_outputs import CausalLMOutputWithPast
             return CausalLMOutputWithPast(loss=None, logits=logits, past_key_values=tuple(pasts))
         return _Output((logits, pasts))
+
+    # ------------------------------------------------------------------ forward() on the fused cache path
+    fused_forward = True        # False: forward() always uses the reference's own 9-tuples (torch.cat growth, per-op launches)
+
+    def _fused_forward_ok(self, input_ids, past_key_values, attention_mask, position_ids, start):
+        """forward() may run on the pre-allocated cache when nothing asks for what only the tuple path offers: CUDA fp16
+        weights, equal-length sequences (no padding mask), default positions, and -- with a past -- one new token."""
+        if not self.fused_forward or not input_ids.is_cuda or not self._fast_ok():
+            return False
+        B, q_len = input_ids.shape
+        if attention_mask is not None and (attention_mask.dim() != 2 or not bool(attention_mask.to(torch.bool).all())):
+            return False
+        if position_ids is not None:
+            exp = torch.arange(start, start + q_len, device=position_ids.device).unsqueeze(0).expand(B, -1)
+            if position_ids.shape != exp.shape or not bool((position_ids == exp).all()):
+                return False
+        if past_key_values is None:
+            return True
+        if q_len != 1 or len(past_key_values) != len(self.model.layers):
+            return False
+        if isinstance(past_key_values[0], KiviPast):
+            return all(isinstance(p, KiviPast) and p.cache is self.cache and p.kv_len == self.cache.kv_len
+                       for p in past_key_values)
+        return past_key_values[0][5] is not None and past_key_values[0][5].shape[0] == B      # plain 9-tuples: import once
+
+    def _forward_fused(self, input_ids, past_key_values, start):
+        B, q_len = input_ids.shape
+        n_layers = len(self.model.layers)
+        reserve = int(getattr(self.config, "kivi_cache_reserve", 1024))      # head-room allocated beyond the current length
+        if past_key_values is None:                                          # prefill into the blocked cache
+            if self.cache is None or self.cache.batch != B or self.cache.max_tokens < q_len + 1:
+                self.init_cache(B, q_len + reserve)
+            positions = torch.arange(q_len, device=input_ids.device).unsqueeze(0).expand(B, -1)
+            h, _ = self._run_layers(input_ids, positions, [(self.cache, i) for i in range(n_layers)])
+            self._pos.fill_(q_len)
+            logits = self.lm_head(h).float()
+        else:
+            if not isinstance(past_key_values[0], KiviPast):                 # a cache grown elsewhere (reference hook): one re-layout
+                self.import_cache(past_key_values, max_tokens=start + reserve)
+            elif self.cache.kv_len + 1 > self.cache.max_tokens:              # out of room: re-allocate at twice the size
+                tuples = [self.cache.export(i) for i in range(n_layers)]
+                self.import_cache(tuples, max_tokens=2 * self.cache.max_tokens)
+            logits = self.decode_step(input_ids).unsqueeze(1).clone()
+        kv = self.cache.kv_len
+        return logits, [KiviPast(self.cache, i, kv) for i in range(n_layers)]
 
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None,
                                       **kwargs):
@@ -466,8 +552,8 @@ class LlamaForCausalLM_KIVI(nn.Module):
         """Continue on the fused path from the reference's per-layer 9-tuples (models/llama_kivi.py:454-455)."""
         seen = past_key_values[0][-1]
         B = past_key_values[0][5].shape[0]
-        if self.cache is None or self.cache.batch != B or (max_tokens or 0) > self.cache.max_tokens:
-            self.init_cache(B, max_tokens or seen + 1024)
+        if self.cache is None or self.cache.batch != B or max(max_tokens or 0, seen + 1) > self.cache.max_tokens:
+            self.init_cache(B, max(max_tokens or 0, seen + 1024))
         for i, past in enumerate(past_key_values):
             self.cache.import_tuple(i, past)
         self._pos.fill_(seen)

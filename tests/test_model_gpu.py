@@ -49,6 +49,7 @@ def test_fused_model_matches_tuple_model(name, kw):
     cfg = default_config(name, **kw)
     torch.manual_seed(0)
     model = LlamaForCausalLM_KIVI(cfg).half().cuda().eval()
+    model.fused_forward = False                       # forward() = the reference's own 9-tuple path (torch.cat growth, per-op launches)
     B, n, steps = 2, 150, 40
     ids = torch.randint(0, cfg.vocab_size, (B, n), device="cuda")
     # tuple path
@@ -80,6 +81,69 @@ def test_fused_model_matches_tuple_model(name, kw):
         else:
             assert torch.equal(tup[i], ref_t[i].view_as(tup[i])), f"tuple[{i}]"
     assert tup[8] == ref_t[8]
+
+
+def test_forward_loop_runs_on_the_fused_cache():
+    """The reference's calling convention -- `out = model(input_ids=..., past_key_values=out.past_key_values)` in a loop,
+    models/llama_kivi.py:815-905 -- lands on the pre-allocated cache: the per-layer past is a KiviPast view ([-1] =
+    kv_seq_len, tensors exported on access), logits equal the decode_step path bit for bit, a cache grown by the tuple path is
+    imported once and continued, and anything the fused path does not cover (padding mask) falls back to real 9-tuples."""
+    from kivi_b200.llama_kivi import KiviPast, LlamaForCausalLM_KIVI, default_config
+    cfg = default_config("tiny", num_attention_heads=4, num_key_value_heads=2, hidden_size=512)
+    torch.manual_seed(3)
+    model = LlamaForCausalLM_KIVI(cfg).half().cuda().eval()
+    B, n = 2, 140
+    ids = torch.randint(0, cfg.vocab_size, (B, n), device="cuda")
+    out = model(input_ids=ids)
+    logits, past = out
+    assert logits.shape == (B, n, cfg.vocab_size) and logits.dtype == torch.float32
+    assert all(isinstance(p_, KiviPast) for p_ in past) and past[0][-1] == n and len(past[0]) == 9
+    inp = model.prepare_inputs_for_generation(torch.cat([ids, logits[:, -1].argmax(-1, keepdim=True)], 1), past_key_values=past)
+    assert inp["input_ids"].shape == (B, 1)
+    # the same steps through decode_step on a second model object with the same weights
+    twin = LlamaForCausalLM_KIVI(cfg).half().cuda().eval()
+    twin.load_state_dict(model.state_dict())
+    twin.init_cache(B, n + 64)
+    l2 = twin.prefill(ids)
+    assert torch.allclose(l2, logits[:, -1], rtol=1e-2, atol=1e-2)      # lm_head on [B, n, hid] vs [B, hid]: other GEMM shape
+    tok = logits[:, -1].argmax(-1, keepdim=True)
+    for step in range(20):
+        logits, past = model(input_ids=tok, past_key_values=past)
+        l2 = twin.decode_step(tok)
+        assert logits.shape == (B, 1, cfg.vocab_size) and torch.equal(logits[:, 0], l2), step
+        tok = logits[:, -1].argmax(-1, keepdim=True)
+    assert past[0][8] == n + 20
+    snap = past[1]
+    fields = snap.materialise()                                        # a 9-tuple snapshot of layer 1
+    assert fields[8] == n + 20 and fields[5].shape[2] == min(n + 20, cfg.residual_length)
+    old_view = past[0]
+    logits, past = model(input_ids=tok, past_key_values=past)          # the cache moves on: unmaterialised older views are stale
+    with pytest.raises(RuntimeError, match="stale"):
+        old_view[0]
+    assert snap[4] is fields[4]                                        # the materialised snapshot stays readable
+    # a cache grown on the tuple path continues on the fused path after one import
+    model.fused_forward = False
+    lt, tp = model(input_ids=ids)
+    assert isinstance(tp[0], tuple) and not isinstance(tp[0], KiviPast)
+    tok_t = lt[:, -1].argmax(-1, keepdim=True)
+    lt, tp = model(input_ids=tok_t, past_key_values=tp)
+    model.fused_forward = True
+    tok_t = lt[:, -1].argmax(-1, keepdim=True)
+    lf, fp_ = model(input_ids=tok_t, past_key_values=tp)               # plain tuples in -> imported -> KiviPast out
+    model.fused_forward = False
+    lt2, tp2 = model(input_ids=tok_t, past_key_values=tp)
+    assert isinstance(fp_[0], KiviPast) and fp_[0][-1] == tp2[0][-1] == n + 2
+    d = (lf - lt2).abs().max().item()
+    assert d <= 3e-2 * lt2.abs().max().item() + 3e-2, d
+    for i in (0, 2, 3, 4, 6, 7):
+        a, b = fp_[0][i], tp2[0][i]
+        assert (a is None and b is None) or torch.equal(a, b.view_as(a)), i
+    # a padding mask is outside the fused path: real 9-tuples come back
+    model.fused_forward = True
+    mask = torch.ones(B, n, dtype=torch.long, device="cuda")
+    mask[0, :5] = 0
+    lm, pm = model(input_ids=ids, attention_mask=mask)
+    assert not isinstance(pm[0], KiviPast) and pm[0][8] == n
 
 
 def test_generate_runs():

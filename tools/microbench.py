@@ -201,7 +201,8 @@ def reference_part(a, res, gen, flush, dev, q, pq, bytes_qk, bytes_sv):
             kc2 = kc.reshape(-1, D, kc.shape[-1]).transpose(1, 2).contiguous()
             ks2 = ks.reshape(-1, D, ks.shape[-1]).transpose(1, 2).contiguous()
             kz2 = kz.reshape(-1, D, kz.shape[-1]).transpose(1, 2).contiguous()
-            ms, _ = timeit_graph(lambda: refmod.gemv_forward_cuda_outer_dim(q2, kc2, ks2, kz2, bits, g, H, Hkv))
+            # (the reference extension launches on the legacy default stream: not capturable, timed call by call)
+            ms, _ = timeit(lambda: refmod.gemv_forward_cuda_outer_dim(q2, kc2, ks2, kz2, bits, g, H, Hkv), flush=flush, iters=10)
             res["ref_qk_kernel_ms"] = ms
             res["ref_qk_kernel_GBps"] = bytes_qk / ms / 1e6
             del kc2, ks2, kz2
@@ -209,7 +210,7 @@ def reference_part(a, res, gen, flush, dev, q, pq, bytes_qk, bytes_sv):
             vc2 = vc.reshape(-1, Tv, vc.shape[-1]).transpose(1, 2).contiguous()
             vs2 = vs.reshape(-1, Tv, vs.shape[-1]).transpose(1, 2).contiguous()
             vz2 = vz.reshape(-1, Tv, vz.shape[-1]).transpose(1, 2).contiguous()
-            ms, _ = timeit_graph(lambda: refmod.gemv_forward_cuda_outer_dim(p2, vc2, vs2, vz2, bits, g, H, Hkv))
+            ms, _ = timeit(lambda: refmod.gemv_forward_cuda_outer_dim(p2, vc2, vs2, vz2, bits, g, H, Hkv), flush=flush, iters=10)
             res["ref_sv_kernel_ms"] = ms
             res["ref_sv_kernel_GBps"] = bytes_sv / ms / 1e6
 
