@@ -278,19 +278,40 @@ def run_decode(model_name, B, seq, K, W, rank, ws, local, sampler=None, e2e=True
     cache = model.cache
     vocab = cfg.vocab_size
     Bg = B * ws
-    model.enable_token_allgather(ws)
     ids = torch.randint(0, vocab, (B, 1), device=dev)
     collective = "none (1 GPU)"
-    try:
-        model.decode_step(ids)                               # warm-up step 1: captures the graph (NCCL all-gather inside)
-        if ws > 1:
-            collective = "NCCL all_gather_into_tensor of the sampled ids (8 B / sequence) inside the step's CUDA graph"
-    except Exception as exc:                                 # capture of the collective refused: gather after the replay
-        if ws == 1:
-            raise
-        model.enable_token_allgather(ws, in_graph=False)
-        model.decode_step(ids)
-        collective = f"NCCL all_gather_into_tensor of the sampled ids after the graph replay (capture failed: {type(exc).__name__})"
+    # N > 1: the ids of all replicas are exchanged inside the step's CUDA graph.  Preferred: the sampling kernel stores them
+    # into the peers' symmetric buffers itself (one fused argmax + all-gather kernel over NVLink); else NCCL inside the graph;
+    # else NCCL after the replay.  Whatever runs is named in the JSON line.
+    attempts = [("p2p", True, "fused argmax + peer stores of the sampled ids (8 B / sequence) into every rank's symmetric buffer "
+                              "(kivi_greedy_sample_exchange_f32 over NVLink, torch symmetric memory), inside the step's CUDA graph"),
+                ("nccl", True, "NCCL all_gather_into_tensor of the sampled ids (8 B / sequence) inside the step's CUDA graph"),
+                ("nccl", False, "NCCL all_gather_into_tensor of the sampled ids after the graph replay")] if ws > 1 else [("nccl", True, collective)]
+    if os.environ.get("KIVI_BENCH_COLLECTIVE") == "nccl":
+        attempts = attempts[1:]
+    last_exc = None
+    for mode, in_graph, text in attempts:
+        try:
+            ok = torch.ones(1, device=dev)
+            try:
+                model.enable_token_allgather(ws, in_graph=in_graph, mode=mode)
+                model.decode_step(ids)                       # warm-up step 1: captures the graph
+            except Exception as exc:                         # this rank failed: tell the others, all fall back together
+                last_exc = exc
+                ok.zero_()
+            if ws > 1:
+                import torch.distributed as td
+                td.all_reduce(ok, op=td.ReduceOp.MIN)
+            if float(ok.item()) > 0:
+                collective = text
+                break
+            model._graph = None
+            collective = None
+        except Exception as exc:
+            last_exc = exc
+            collective = None
+    if collective is None:
+        raise RuntimeError(f"no token exchange worked: {last_exc}")
     for _ in range(W - 1):
         model.decode_step()                                  # feeds back its own sampled ids
     torch.cuda.synchronize()
@@ -437,7 +458,8 @@ def reference_gpu_timing(B, H, Hkv, T, bits, g, R):
 # main arm
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
-    os.environ.setdefault("NCCL_DEBUG", "WARN")              # keep NCCL's version banner off stdout: one JSON line only
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / logs go to stderr: stdout carries ONE JSON line
     import gc
     import torch
     from kivi_b200 import dist as kdist

@@ -250,6 +250,18 @@ int kivi_rope_split_f16(const void* qkv, const void* cos_table, const void* sin_
                         void* stream);
 int kivi_silu_mul_f16(const void* gate_up, void* out, int rows, int intermediate, void* stream);
 
+/* Greedy sampling fused with its collective (the only exchange of the data-parallel decode; the reference has
+ * none).  next_local[b] = argmax_v logits[b, v] (first index among equal maxima, as torch.argmax; logits fp32 [batch, vocab],
+ * models/llama_kivi.py:881); ids_feedback (may be NULL) receives the same ids (the next step's input buffer).
+ * peer_buffers: NULL (one GPU), or a DEVICE array of `world` pointers, entry p = rank p's exchange buffer -- one symmetric
+ * allocation per rank (peer-mapped over NVLink / NVSwitch), laid out as int64 tokens[2][world * batch] followed by
+ * uint64 arrived[world], zero-initialised.  The kernel stores its ids into slot [step & 1][rank * batch + b] of EVERY rank's
+ * buffer with plain peer stores, releases arrived[rank] on every peer, and waits (bounded, *err = 1 on time-out) until the
+ * ids of all ranks for this step have arrived in its own buffer.  `step` is a device int32 the caller increments before each
+ * call (the same on all ranks); all calls are CUDA-graph capturable. */
+int kivi_greedy_sample_exchange_f32(const void* logits, int batch, int vocab, void* next_local, void* ids_feedback,
+                                    const void* peer_buffers, int rank, int world, const void* step, void* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,9 +106,86 @@ silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int I)
     *reinterpret_cast<__half2*>(out + (int64_t)row * I + i) = __hmul2_rn(a, u);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Greedy sampling fused with its collective.  One block per sequence: argmax over the vocabulary (first index among equal
+// maxima, like torch.argmax), then thread 0 stores the id into this rank's slot of EVERY rank's token buffer -- plain stores
+// to peer memory over NVLink / NVSwitch (the buffers are one symmetric allocation, torch.distributed._symmetric_memory) --
+// and releases a per-rank arrival counter on every peer.  Block 0 then waits (bounded) until all ranks' ids of this step have
+// arrived here.  Argmax is local to a sequence, so the data-parallel replicas exchange 8 bytes per sequence and nothing of
+// the next step depends on the exchange: no rank ever blocks another one's critical path.
+//   peer[p]  : rank p's buffer: int64 tokens[2][world * B] (double-buffered by step parity), then uint64 arrived[world]
+//   step     : device counter, incremented by the caller BEFORE the launch (inside the same CUDA graph)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+greedy_exchange_kernel(const float* __restrict__ logits, int V, long long* __restrict__ next_local, long long* __restrict__ ids_feedback,
+                       long long* const* __restrict__ peer, int B, int rank, int world, const int* __restrict__ step_ptr, int* __restrict__ err)
+{
+    __shared__ float smax[8];
+    __shared__ int sidx[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* row = logits + (long long)b * V;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += 256) {
+        const float v = row[i];
+        if (v > best || (v == best && i < bi) || (v != v && !(best != best))) { best = v; bi = i; }   // a NaN wins, like torch.argmax
+    }
+    #pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const bool take = (ov != ov) ? (!(best != best) || oi < bi) : (!(best != best) && (ov > best || (ov == best && oi < bi)));
+        if (take) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { smax[tid >> 5] = best; sidx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            const float ov = smax[w];
+            const int oi = sidx[w];
+            const bool take = (ov != ov) ? (!(best != best) || oi < bi) : (!(best != best) && (ov > best || (ov == best && oi < bi)));
+            if (take) { best = ov; bi = oi; }
+        }
+        const long long tok = bi;
+        next_local[b] = tok;
+        if (ids_feedback) ids_feedback[b] = tok;
+        if (peer) {
+            const int step = *step_ptr;
+            const long long slot = (long long)(step & 1) * world * B + (long long)rank * B + b;
+            for (int p = 0; p < world; ++p) peer[p][slot] = tok;
+            __threadfence_system();                                         // the ids are visible system-wide before the arrivals
+            for (int p = 0; p < world; ++p)
+                atomicAdd_system(reinterpret_cast<unsigned long long*>(peer[p] + 2ll * world * B + rank), 1ull);
+        }
+    }
+    if (peer && b == 0 && tid < world) {                                     // all ranks' ids of this step are here before the kernel ends
+        const unsigned long long want = (unsigned long long)(*step_ptr) * (unsigned long long)B;
+        const volatile unsigned long long* cnt = reinterpret_cast<const volatile unsigned long long*>(peer[rank] + 2ll * world * B + tid);
+        long long spins = 0;
+        while (*cnt < want) {
+            if (++spins > (1ll << 24)) { *err = 1; break; }                  // ~ a second: a peer is gone; report instead of hanging the GPU
+            __nanosleep(64);
+        }
+        __threadfence_system();
+    }
+}
+
 }  // namespace kivi
 
 using namespace kivi;
+
+extern "C" int kivi_greedy_sample_exchange_f32(const void* logits, int batch, int vocab, void* next_local, void* ids_feedback,
+                                               const void* peer_buffers, int rank, int world, const void* step, void* err,
+                                               void* stream)
+{
+    if (!logits || !next_local) return KIVI_ERR_NULL;
+    if (batch <= 0 || vocab <= 0) return KIVI_ERR_SHAPE;
+    if (peer_buffers && (!step || !err || world < 1 || rank < 0 || rank >= world || world > 256)) return KIVI_ERR_SHAPE;
+    greedy_exchange_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, vocab, (long long*)next_local, (long long*)ids_feedback, (long long* const*)peer_buffers,
+        batch, rank, world, (const int*)step, (int*)err);
+    return post_launch();
+}
 
 extern "C" int kivi_add_rmsnorm_f16(const void* x, void* residual, const void* weight, void* out,
                                     int rows, int hidden, float eps, void* stream)

@@ -88,6 +88,34 @@ def gather_tokens(local_tokens: torch.Tensor, out: torch.Tensor | None = None) -
     return out
 
 
+class PeerTokenExchange:
+    """The token exchange of greedy data-parallel decoding WITHOUT a library collective: every rank owns one symmetric buffer
+    (torch.distributed._symmetric_memory: peer-mapped over NVLink / NVSwitch), and the sampling kernel
+    (kivi_greedy_sample_exchange_f32) stores its ids straight into every peer's buffer and signals arrival counters -- the
+    compute step (argmax) and its collective (all-gather of the ids) are ONE kernel, capturable in the step's CUDA graph.
+    Layout per rank: int64 tokens[2][world * B] (double-buffered by step parity) + uint64 arrived[world]."""
+
+    def __init__(self, batch: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.batch = dist.get_world_size(), dist.get_rank(), batch
+        n = 2 * self.world * batch + self.world
+        self.buf = symm.empty(n, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.peer_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)      # incremented inside the step, before the kernel
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier()                                                    # every rank's buffer is zeroed before anyone signals
+
+    def tokens(self) -> torch.Tensor:
+        """[world * B] ids of the last completed step (synchronises: reads the device step counter)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("kivi_b200: the peer token exchange timed out waiting for another rank")
+        par = int(self.step.item()) & 1
+        return self.buf[par * self.world * self.batch: (par + 1) * self.world * self.batch]
+
+
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

@@ -19,6 +19,7 @@ def _bind():
     _lib.bind("kivi_add_rmsnorm_f16", i32, [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp])
     _lib.bind("kivi_rope_split_f16", i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp])
     _lib.bind("kivi_silu_mul_f16", i32, [vp, vp, i32, i32, vp])
+    _lib.bind("kivi_greedy_sample_exchange_f32", i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp])
     _B = True
 
 
@@ -47,3 +48,18 @@ def silu_mul(gate_up, out):
     _lib.check(_lib.lib().kivi_silu_mul_f16(gate_up.data_ptr(), out.data_ptr(), rows, inter,
                                             _lib.stream_ptr(out.device)), "kivi_silu_mul_f16")
     return out
+
+
+def greedy_sample(logits, next_local, ids_feedback=None, exchange=None):
+    """next_local[b] = argmax(logits[b]) (+ copy into ids_feedback); with `exchange` (kivi_b200.dist.PeerTokenExchange) the
+    same kernel also stores the ids into every rank's token buffer over NVLink and waits for the other ranks' ids."""
+    _bind()
+    B, V = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and next_local.dtype == torch.int64
+    ex = exchange
+    _lib.check(_lib.lib().kivi_greedy_sample_exchange_f32(
+        logits.data_ptr(), B, V, next_local.data_ptr(), ids_feedback.data_ptr() if ids_feedback is not None else None,
+        ex.peer_ptrs.data_ptr() if ex is not None else None, ex.rank if ex is not None else 0, ex.world if ex is not None else 1,
+        ex.step.data_ptr() if ex is not None else None, ex.err.data_ptr() if ex is not None else None,
+        _lib.stream_ptr(logits.device)), "kivi_greedy_sample_exchange_f32")
+    return next_local

@@ -347,6 +347,7 @@ class LlamaForCausalLM_KIVI(nn.Module):
         self._fast = None
         self._dist_tokens = None            # [world * B] ids gathered inside the step (greedy sampling, world > 1)
         self._dist_in_graph = True
+        self._exchange = None               # kivi_b200.dist.PeerTokenExchange: ids stored into the peers' buffers by the sampling kernel
 
     # ------------------------------------------------------------------ HF-style construction
     @classmethod
@@ -594,23 +595,34 @@ class LlamaForCausalLM_KIVI(nn.Module):
         self._pos.add_(1)
         # greedy sampling inside the step (and inside its CUDA graph): the argmax of a sequence needs only that
         # sequence's logits, so with data-parallel replicas the exchange is the sampled ids, 8 B per sequence
-        torch.argmax(self._logits, dim=-1, out=self.next_tokens)
-        self._ids.copy_(self.next_tokens.view(-1, 1))        # decode_step() without ids continues with the sampled ones
+        from . import glue
+        if self._exchange is not None:
+            self._exchange.step.add_(1)                      # the step number the peers' arrival counters are compared with
+        # one kernel: argmax per sequence, the feed-back copy for the next step, and (replicas) the ids stored straight into
+        # every peer's buffer over NVLink + arrival counters
+        glue.greedy_sample(self._logits, self.next_tokens, self._ids.view(-1), self._exchange)
         if self._dist_tokens is not None and self._dist_in_graph:
             from . import dist as kdist
             kdist.gather_tokens(self.next_tokens, out=self._dist_tokens)
 
-    def enable_token_allgather(self, world_size: int, in_graph: bool = True):
-        """Data-parallel replicas (kivi_b200.dist): gather every rank's sampled ids into `all_tokens`
-        [world_size * B] -- inside the decode step and its CUDA graph (in_graph, the default), or right after the
-        replay.  Call before the first decode_step (the step is captured once)."""
-        self._dist_tokens = torch.zeros(world_size * self.cache.batch, dtype=torch.long, device=self.cache.device) \
-            if world_size > 1 else None
+    def enable_token_allgather(self, world_size: int, in_graph: bool = True, mode: str = "nccl"):
+        """Data-parallel replicas (kivi_b200.dist): every rank's sampled ids end up in `all_tokens` [world_size * B].
+        mode "p2p": the sampling kernel itself stores the ids into every peer's symmetric buffer (PeerTokenExchange; one
+        fused compute + collective kernel inside the step's CUDA graph).  mode "nccl": an NCCL all-gather of the ids, inside
+        the graph (in_graph) or right after the replay.  Call before the first decode_step (the step is captured once)."""
+        self._exchange, self._dist_tokens = None, None
+        if world_size > 1 and mode == "p2p":
+            from . import dist as kdist
+            self._exchange = kdist.PeerTokenExchange(self.cache.batch, self.cache.device)
+        elif world_size > 1:
+            self._dist_tokens = torch.zeros(world_size * self.cache.batch, dtype=torch.long, device=self.cache.device)
         self._dist_in_graph = in_graph
         self._graph = None
 
     @property
     def all_tokens(self):
+        if self._exchange is not None:
+            return self._exchange.tokens()
         return self.next_tokens if self._dist_tokens is None else self._dist_tokens
 
     def _fast_ok(self):
