@@ -52,6 +52,14 @@ constexpr int kChunkUnroll = KIVI_UNROLL;
 #ifndef KIVI_SHIFT_IMAD
 #define KIVI_SHIFT_IMAD 0
 #endif
+// 1: the p.V kernel does not wait for the whole q.K^T grid (griddepcontrol.wait) but, unit by unit, for the q.K^T ranges of
+// that unit (release / acquire counters in the workspace): a p.V CTA starts working the moment ITS SM's q.K^T CTA has left,
+// while slower SMs are still in their q.K^T tail.  Correct (tests pass in both modes) but MEASURED SLOWER: the release fence
+// of every (warp, unit) visit of q.K^T and the acquire round trip of every p.V visit cost more than the hand-over they
+// save (cfg 2: 0.0992 vs 0.0953 ms per call, cfg 3 0.137 vs 0.131, B = 128 0.346 vs 0.334; gpurun_out/r2m).
+#ifndef KIVI_UNIT_FLAGS
+#define KIVI_UNIT_FLAGS 0
+#endif
 
 namespace kivi {
 
@@ -103,6 +111,7 @@ struct Workspace {                     // carved from the caller's buffer (kivi_
     float2* stats; int stat_cap;       // [B*H][stat_cap] (max, sum exp(x - max)) per qk item
     float* part; int part_cap;         // [n_units][part_cap][G][2][128] partial outputs (packed | window)
     int* count;                        // [n_units] arrivals of sv ranges; the last arriver resets it to 0
+    int* ready;                        // [n_units] q.K^T ranges of the unit that have published logits + statistics (reset by the finaliser)
 };
 
 struct AttnParams {
@@ -910,6 +919,11 @@ qk_kernel(const AttnParams p)
             warp_max_sum(m, sm, M, S);
             if (lane == 0) p.w.stats[(int64_t)(uq0 + h) * p.w.stat_cap + (gw - w_first)] = make_float2(M, S);
         }
+#if KIVI_UNIT_FLAGS
+        // publish: this range's logits (all lanes) and statistics of the unit happen-before the counter increment
+        __syncwarp();
+        if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.w.ready + unit) : "memory");
+#endif
         (void)j_first;
         left -= n_here;
         if (j == s.ipu) { j = 0; ++unit; }
@@ -920,15 +934,33 @@ qk_kernel(const AttnParams p)
 // ------------------------------------------------------------------------------------------------
 // p . V  (+ softmax normalisation, output, cache update)
 // ------------------------------------------------------------------------------------------------
+// wait until every q.K^T range of unit `un` has published its logits and statistics (all lanes call; lane 0 spins)
+__device__ __forceinline__ void wait_unit_ready(const AttnParams& p, const Sched& s, const Ranges<CostQK>& rq, int un, int lane)
+{
+#if KIVI_UNIT_FLAGS
+    if (lane == 0) {
+        const int need = rq.owner(un, s.ipu - 1) - rq.owner(un, 0) + 1;
+        int have;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(p.w.ready + un) : "memory");
+            if (have < need) __nanosleep(40);
+        } while (have < need);
+        asm volatile("fence.proxy.async;" ::: "memory");          // the bulk copies (async proxy) that follow read what was just acquired
+    }
+    __syncwarp();
+#endif
+}
+
 template <int VB, int G, int GS>
 __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnParams& p, const Sched& s,
-                                              int ratio, int lane, uint64_t pol)
+                                              int ratio, int lane, uint64_t pol, const Ranges<CostQK>& rq, int& ready_unit)
 {
     const CacheDesc& c = p.c;
     if (cur.left > 0 && cur.j == s.bpu - 1) {                     // the new token needs no load
         cur.j = 0; ++cur.unit; --cur.left;
     }
     if (cur.left <= 0) return;
+    if (cur.unit != ready_unit) { wait_unit_ready(p, s, rq, cur.unit, lane); ready_unit = cur.unit; }
     if (lane == 0) {
         const int u = p.hchunks == 1 ? cur.unit : cur.unit / p.hchunks, hc = p.hchunks == 1 ? 0 : cur.unit % p.hchunks;
         uint8_t* dst = pp.prod();
@@ -1003,6 +1035,7 @@ sv_kernel(const AttnParams p)
     if (!sched_ok(s, c, p.max_kv_len)) return;                               // the q.K^T kernel has flagged state[6]
     KIVI_TL(1, gw, 0);
     const Ranges<CostSV>& rg = rg_sh;                                        // range owners: every range is non-empty
+    const Ranges<CostQK>& rq = rq_sh;                                        // the qk kernel's ranges
     if (gw >= (int)rg.W) return;
     int u_lo, j_lo, u_hi, j_hi;
     rg.lo(gw, u_lo, j_lo); rg.lo(gw + 1, u_hi, j_hi);
@@ -1016,13 +1049,15 @@ sv_kernel(const AttnParams p)
         const int n_slices = 4 * c.B * c.Hkv, n_workers = (int)rg.W;
         for (int sl = gw; sl < n_slices; sl += n_workers) k_flush_slice<KB>(p, s, sl >> 2, sl & 3, lane);
     }
+#if !KIVI_UNIT_FLAGS
     pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
+#endif
+    int ready_unit = -1;                                                     // last unit whose q.K^T ranges are known to be complete
 
     constexpr int NG = Cols<G, GS>::NG;
     const int h_l = t4 % G;
     constexpr int kHalfBytes = kHalfChunks * Lay<VB>::kChunkBytes + kHalfChunks * NG * 64;   // codes + meta of half a V block
     const int rec = G * 2 * kD;                                              // floats of a partial record
-    const Ranges<CostQK>& rq = rq_sh;                                        // the qk kernel's ranges
 
     int unit = u_lo, j = j_lo, left = n_mine;
     // statistics slots of a unit, fetched one unit ahead: lane i holds slot i of every head
@@ -1032,6 +1067,7 @@ sv_kernel(const AttnParams p)
         const int u_ = p.hchunks == 1 ? un : un / p.hchunks, hc_ = p.hchunks == 1 ? 0 : un % p.hchunks;
         const int row0 = u_ * ratio + hc_ * G;
         nstat = rq.owner(un, s.ipu - 1) - rq.owner(un, 0) + 1;
+        if (un != ready_unit) { wait_unit_ready(p, s, rq, un, lane); ready_unit = un; }
         #pragma unroll
         for (int h = 0; h < G; ++h) {
             sn[h] = make_float2(-INFINITY, 0.f);
@@ -1041,7 +1077,7 @@ sv_kernel(const AttnParams p)
     // the few statistics words first, THEN the bulk copies: every warp of the grid issues its first stages at this very
     // moment (~29 MB in flight), and a small load queued behind them would be the last thing to arrive
     fetch_stats(unit);
-    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
+    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
     KIVI_TL(1, gw, 1);
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
     CommitIn pend_cin;
@@ -1051,6 +1087,9 @@ sv_kernel(const AttnParams p)
         const int uq0 = u * ratio + hc * G;
         __syncwarp();                                                        // lane 0's acq_rel arrival covers the other lanes' reads
         if (nparts > 1 && lane == 0) p.w.count[un] = 0;
+#if KIVI_UNIT_FLAGS
+        if (lane == 0) p.w.ready[un] = 0;                                    // every p.V range of the unit has long passed its acquire
+#endif
         float qs[G][4], rs[G][4];
         #pragma unroll
         for (int h = 0; h < G; ++h)
@@ -1171,7 +1210,7 @@ sv_kernel(const AttnParams p)
                     }, acc, zc, lane);
                     __syncwarp();
                     pp.pop();
-                    sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
+                    sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
                 }
                 float zsel[NG];
                 gather_z<G, GS>(zc, lane, zsel);
@@ -1225,7 +1264,7 @@ sv_kernel(const AttnParams p)
                 }
                 __syncwarp();
                 pp.pop();
-                sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol);
+                sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
                 // lane (g8, t): oacc[mt] = D[16mt + g8 | + 8][heads 2t, 2t+1] -> channel order through shared memory
                 #pragma unroll
                 for (int mt = 0; mt < 8; ++mt)
@@ -1316,12 +1355,14 @@ static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, in
     const int64_t o_st = take(rows * stat_cap * 8);
     const int64_t o_pt = take((int64_t)n_units * part_cap * G * 2 * kD * 4);
     const int64_t o_ct = take((int64_t)n_units * 4);
+    const int64_t o_rd = take((int64_t)n_units * 4);
     if (w) {
         uint8_t* b = (uint8_t*)base;
         w->lg = (__half*)(b + o_lg); w->ld = ld;
         w->stats = (float2*)(b + o_st); w->stat_cap = stat_cap;
         w->part = (float*)(b + o_pt); w->part_cap = part_cap;
         w->count = (int*)(b + o_ct);
+        w->ready = (int*)(b + o_rd);
     }
     return off;
 }
