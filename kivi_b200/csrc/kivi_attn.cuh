@@ -52,6 +52,9 @@ constexpr int kChunkUnroll = KIVI_UNROLL;
 #ifndef KIVI_SHIFT_IMAD
 #define KIVI_SHIFT_IMAD 0
 #endif
+#ifndef KIVI_PRED_FINALIZE
+#define KIVI_PRED_FINALIZE 1             // 0: the round-1 epilogue (selects); A/B builds
+#endif
 // 1: the p.V kernel does not wait for the whole q.K^T grid (griddepcontrol.wait) but, unit by unit, for the q.K^T ranges of
 // that unit (release / acquire counters in the workspace): a p.V CTA starts working the moment ITS SM's q.K^T CTA has left,
 // while slower SMs are still in their q.K^T tail.  Correct (tests pass in both modes) but MEASURED SLOWER: the release fence
@@ -301,6 +304,14 @@ __device__ __forceinline__ void gather_z(const float (&zc)[4], int lane, float (
         z += __shfl_xor_sync(0xffffffffu, z, 1);
         z += __shfl_xor_sync(0xffffffffu, z, 2);
     }
+#if KIVI_PRED_FINALIZE
+    if (G == 1 && GS == 32) {                           // finalize() reads zsel[t] only (t = lane & 3): one shuffle, source lane 8t + t
+        const float zt = __shfl_sync(0xffffffffu, z, 9 * (lane & 3));
+        #pragma unroll
+        for (int grp = 0; grp < Cols<G, GS>::NG; ++grp) zsel[grp] = zt;
+        return;
+    }
+#endif
     #pragma unroll
     for (int grp = 0; grp < Cols<G, GS>::NG; ++grp)
         zsel[grp] = __shfl_sync(0xffffffffu, z, 8 * grp + (lane & 3));
@@ -328,7 +339,28 @@ __device__ __forceinline__ void finalize(const float (&acc)[8][4], const float (
     constexpr int GPF = Cols<G, GS>::GPF;
     const int g8 = lane >> 2, t = lane & 3;
     if (G == 1 && GS == 32) {
-        // lane t owns MMAs 2t and 2t+1 (group t): pick them with selects instead of 8 predicated copies of the tail
+        // lane t owns MMAs 2t and 2t+1 (group t).
+#if KIVI_PRED_FINALIZE
+        // Four PREDICATED copies of the eight FADD / FFMA (one per value of t, compile-time accumulator indices and scales):
+        // they run on the FMA pipe, which idles, instead of 33 selects on the ALU pipe, which is the one that binds.
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        #pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (t == v) {
+                const float sl = inv_pos_scale<BITS>(2 * v) * post, sh = inv_pos_scale<BITS>(2 * v + 1) * post, zt = zsel[v] * post;
+                v0 = fmaf(acc[2 * v][0] + acc[2 * v][1], sl, zt);
+                v1 = fmaf(acc[2 * v][2] + acc[2 * v][3], sl, zt);
+                v2 = fmaf(acc[2 * v + 1][0] + acc[2 * v + 1][1], sh, zt);
+                v3 = fmaf(acc[2 * v + 1][2] + acc[2 * v + 1][3], sh, zt);
+            }
+        }
+        const int o = 32 * t + g8;
+        emit(0, o, v0);
+        emit(1, o + 8, v1);
+        emit(2, o + 16, v2);
+        emit(3, o + 24, v3);
+#else
+        // pick them with selects instead of 8 predicated copies of the tail
         const bool t1 = t & 1, t2 = t & 2;
         float lo[4], hi[4];
         #pragma unroll
@@ -344,6 +376,7 @@ __device__ __forceinline__ void finalize(const float (&acc)[8][4], const float (
         emit(1, o + 8, fmaf(lo[2] + lo[3], sl, zt));
         emit(2, o + 16, fmaf(hi[0] + hi[1], sh, zt));
         emit(3, o + 24, fmaf(hi[2] + hi[3], sh, zt));
+#endif
     } else {
         const int gi_l = t / G;
         #pragma unroll

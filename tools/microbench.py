@@ -148,6 +148,10 @@ def fused_part(a, res, gen, flush, dev):
     kk = torch.randn((B, Hkv, nfill, D), generator=gen, device=dev, dtype=torch.float16)
     vv = torch.randn((B, Hkv, nfill, D), generator=gen, device=dev, dtype=torch.float16)
     cache.prefill(0, kk, vv)
+    # prompt -> blocked stores (models/llama_kivi.py:425-452 fused: transpose + quantise + fragment pack of K, pack of V)
+    ms_p, _ = timeit(lambda: cache.prefill(0, kk, vv), flush=flush, iters=5)
+    res["prefill_pack_ms"] = ms_p
+    res["prefill_pack_GBps"] = 2 * B * Hkv * nfill * D * (2 + bits / 8 + 4 / g) / ms_p / 1e6   # fp16 K and V read, packed written
     del kk, vv
     qd = torch.randn((B, H, D), generator=gen, device=dev, dtype=torch.float16)
     kn = torch.randn((B, Hkv, D), generator=gen, device=dev, dtype=torch.float16)
