@@ -413,9 +413,9 @@ __device__ __forceinline__ void walk_slots(const float (&run)[Slots<G, GS>::k], 
 }
 
 // quantise one value with its group's (min, scale): quant/new_pack.py:238-241 (rint follows)
-__device__ __forceinline__ float q_code(float x, float mnf, float scf, float maxq) {
+__device__ __forceinline__ float q_code(float x, float mnf, float scf, float rcp, float maxq) {
     const __half t1 = __float2half_rn(x - mnf);
-    const __half t2 = __float2half_rn(__fdiv_rn(__half2float(t1), scf));
+    const __half t2 = quot_to_half(__half2float(t1), scf, rcp);
     return fminf(fmaxf(__half2float(t2), 0.f), maxq);
 }
 
@@ -466,10 +466,10 @@ __device__ __noinline__ void commit_unit(const AttnParams& p, const Sched& s, in
         }
         const __half d16 = __float2half_rn(mxf - mnf);
         const __half sc = __float2half_rn(__fdiv_rn(__half2float(d16), maxq));
-        const float scf = __half2float(sc);
+        const float scf = __half2float(sc), rcp = __frcp_rn(scf);
         uint32_t four = 0;
         #pragma unroll
-        for (int e = 0; e < 4; ++e) four |= (uint32_t)__float2int_rn(q_code(x[e], mnf, scf, maxq)) << (8 * e);
+        for (int e = 0; e < 4; ++e) four |= (uint32_t)__float2int_rn(q_code(x[e], mnf, scf, rcp, maxq)) << (8 * e);
         __syncwarp();
         reinterpret_cast<uint32_t*>(scratch)[lane] = four;                              // codes[channel] as bytes
         if (lane % lpg == 0) {
@@ -551,7 +551,7 @@ __device__ __noinline__ void k_flush_slice(const AttnParams& p, const Sched& s, 
             mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, 16)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 16));
             const __half sc0 = __float2half_rn(__fdiv_rn(__half2float(__float2half_rn(mx0 - mn0)), maxq));
             const __half sc1 = __float2half_rn(__fdiv_rn(__half2float(__float2half_rn(mx1 - mn1)), maxq));
-            const float scf0 = __half2float(sc0), scf1 = __half2float(sc1);
+            const float scf0 = __half2float(sc0), scf1 = __half2float(sc1), rcp0 = __frcp_rn(scf0), rcp1 = __frcp_rn(scf1);
             const int og = o0 + gl * g;                                                 // outer index of the group's first token
             if (hw == 0) {                                                              // meta entry half: { z, z', s, s' } of the pair
                 __align__(8) __half mz[4] = {__float2half_rn(mn0), __float2half_rn(mn1), sc0, sc1};
@@ -577,8 +577,8 @@ __device__ __noinline__ void k_flush_slice(const AttnParams& p, const Sched& s, 
                 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     const float2 f = __half22float2(v[m]);
-                    const uint32_t c0 = (uint32_t)__float2int_rn(q_code(f.x, mn0, scf0, maxq));
-                    const uint32_t c1 = (uint32_t)__float2int_rn(q_code(f.y, mn1, scf1, maxq));
+                    const uint32_t c0 = (uint32_t)__float2int_rn(q_code(f.x, mn0, scf0, rcp0, maxq));
+                    const uint32_t c1 = (uint32_t)__float2int_rn(q_code(f.y, mn1, scf1, rcp1, maxq));
                     words[m] = (words[m] & keep) | ((c0 | (c1 << 16)) << (KB * j));
                 }
             }

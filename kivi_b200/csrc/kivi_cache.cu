@@ -11,9 +11,9 @@
 namespace kivi {
 
 // same arithmetic as kivi_pack.cu (quant/new_pack.py:238-241)
-__device__ __forceinline__ uint32_t q_one(float x, float mnf, float scf, float maxq) {
+__device__ __forceinline__ uint32_t q_one(float x, float mnf, float scf, float rcp, float maxq) {
     const __half t1 = __float2half_rn(x - mnf);
-    const __half t2 = __float2half_rn(__fdiv_rn(__half2float(t1), scf));
+    const __half t2 = quot_to_half(__half2float(t1), scf, rcp);
     float f = __half2float(t2);
     f = fminf(fmaxf(f, 0.f), maxq);
     return (uint32_t)__float2int_rn(f);
@@ -61,8 +61,8 @@ block_prefill_kernel(CacheDesc c, const __half* __restrict__ x, int n, int nq)
         float mnf = val(inner, G * g), mxf = mnf;
         for (int i = 1; i < g; ++i) { const float v = val(inner, G * g + i); mnf = fminf(mnf, v); mxf = fmaxf(mxf, v); }
         const __half sc = scale_of(mnf, mxf, maxq);
-        const float scf = __half2float(sc);
-        for (int i = 0; i < g; ++i) codes[inner][G * g + i] = (uint8_t)q_one(val(inner, G * g + i), mnf, scf, maxq);
+        const float scf = __half2float(sc), rcp = __frcp_rn(scf);
+        for (int i = 0; i < g; ++i) codes[inner][G * g + i] = (uint8_t)q_one(val(inner, G * g + i), mnf, scf, rcp, maxq);
         *reinterpret_cast<__half*>(blkp + lay_scale_off(BITS, g, inner, G)) = sc;
         *reinterpret_cast<__half*>(blkp + lay_zero_off(BITS, g, inner, G)) = __float2half_rn(mnf);
     }

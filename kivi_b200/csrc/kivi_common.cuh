@@ -103,6 +103,20 @@ __device__ __forceinline__ float field_rescale(int i) {
     return __uint_as_float((uint32_t)(127 + 59 - Unpack<BITS>::pos(i)) << 23);
 }
 
+// fp16( fp32(a / s) ) -- the reference's `data.div_(scale)` on fp16 tensors (quant/new_pack.py:240: ATen divides in fp32 and
+// rounds to fp16) -- bit-exact WITHOUT the IEEE division in the common case.  r = RN32(1 / s) (per group, __frcp_rn); q' = a * r
+// is within 2 ulp of RN32(a / s), so both round to the same fp16 unless q' lies within a few ulp of an fp16 rounding boundary
+// (the 13 dropped mantissa bits == 0x1000); only then -- about one element in a thousand -- or in the fp16 subnormal range, or
+// for NaN (0 / 0 of a flat group) the exact division runs.  The division was ~half of the ~35 instructions a quantised element
+// costs; every pack path (public pack, prefill, K flush, V token) is bound by that arithmetic, not by HBM.
+__device__ __forceinline__ __half quot_to_half(float a, float s, float r) {
+    float q = a * r;
+    const uint32_t b = __float_as_uint(q);
+    const bool sure = ((b & 0x1fffu) - 0x0ffcu > 8u) && (q >= 6.103515625e-05f || q == 0.f);
+    if (!sure) q = __fdiv_rn(a, s);
+    return __float2half_rn(q);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
     #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

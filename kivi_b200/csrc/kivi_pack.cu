@@ -10,9 +10,9 @@
 
 namespace kivi {
 
-__device__ __forceinline__ uint32_t quantize_one(float x, float mnf, float scf, float maxq) {
+__device__ __forceinline__ uint32_t quantize_one(float x, float mnf, float scf, float rcp, float maxq) {
     const __half t1 = __float2half_rn(x - mnf);                                   // :239
-    const __half t2 = __float2half_rn(__fdiv_rn(__half2float(t1), scf));          // :240 (IEEE divide)
+    const __half t2 = quot_to_half(__half2float(t1), scf, rcp);                   // :240 (= fp16 of the IEEE fp32 quotient)
     float f = __half2float(t2);
     f = fminf(fmaxf(f, 0.f), maxq);                                               // :241 clamp (NaN -> 0)
     return (uint32_t)__float2int_rn(f);                                           // round half even
@@ -71,10 +71,10 @@ pack_lastdim_kernel(const __half* __restrict__ x, int64_t n_words, int lpg_log2,
     if (!active) return;
     const __half d = __float2half_rn(mxf - mnf);                                   // :238
     const __half sc = __float2half_rn(__fdiv_rn(__half2float(d), maxq));           // :238
-    const float scf = __half2float(sc);
+    const float scf = __half2float(sc), rcp = __frcp_rn(scf);
     uint32_t word = 0;
     #pragma unroll
-    for (int j = 0; j < FPI; ++j) word |= quantize_one(v[j], mnf, scf, maxq) << (BITS * j);
+    for (int j = 0; j < FPI; ++j) word |= quantize_one(v[j], mnf, scf, rcp, maxq) << (BITS * j);
     code[wid] = (int32_t)word;
     if ((wid & ((1 << lpg_log2) - 1)) == 0) {
         const int64_t gid = wid >> lpg_log2;
@@ -97,7 +97,7 @@ pack_lastdim_generic_kernel(const __half* __restrict__ x, int64_t n_words, int g
     const float maxq = (float)((1 << BITS) - 1);
     uint32_t word = 0;
     int64_t last_gid = -1;
-    float mnf = 0.f, scf = 0.f;
+    float mnf = 0.f, scf = 0.f, rcp = 0.f;
     for (int j = 0; j < FPI; ++j) {
         const int64_t e = wid * FPI + j;
         const int64_t gid = e / g;
@@ -109,10 +109,11 @@ pack_lastdim_generic_kernel(const __half* __restrict__ x, int64_t n_words, int g
             const __half d = __float2half_rn(mxf - mnf);
             const __half sc = __float2half_rn(__fdiv_rn(__half2float(d), maxq));
             scf = __half2float(sc);
+            rcp = __frcp_rn(scf);
             if (e == gid * g) { scale[gid] = sc; mn_out[gid] = __float2half_rn(mnf); }
             last_gid = gid;
         }
-        word |= quantize_one(__half2float(x[e]), mnf, scf, maxq) << (BITS * j);
+        word |= quantize_one(__half2float(x[e]), mnf, scf, rcp, maxq) << (BITS * j);
     }
     code[wid] = (int32_t)word;
 }
