@@ -63,10 +63,6 @@ constexpr int kChunkUnroll = KIVI_UNROLL;
 #ifndef KIVI_EARLY_COMMIT
 #define KIVI_EARLY_COMMIT 1              // 1: the units' cache updates run at the START of the p.V kernel (spread over its warps); 0: in the last arriver
 #endif
-#ifndef KIVI_SV_PREFETCH
-#define KIVI_SV_PREFETCH 0               // 1: the p.V kernel's first cache blocks go in flight before its grid-dependency wait (measured: no gain,
-                                         // the copies compete with the q.K^T stragglers that the wait is waiting for)
-#endif
 #ifndef KIVI_UNIT_FLAGS
 #define KIVI_UNIT_FLAGS 0
 #endif
@@ -991,12 +987,7 @@ __device__ __forceinline__ void wait_unit_ready(const AttnParams& p, const Sched
 #endif
 }
 
-// PART = kIssueAll: the whole stage-item.  The first stages of a warp are issued in two parts around the grid-dependency
-// wait: kIssueCache = what lies in the cache (packed V block or window rows: nothing the q.K^T kernel writes), transaction
-// bytes announced WITHOUT the arrival; kIssueLogits = the item's logits rows and the arrival that lets the phase complete.
-enum { kIssueAll = 0, kIssueCache = 1, kIssueLogits = 2 };
-
-template <int VB, int G, int GS, int PART = kIssueAll>
+template <int VB, int G, int GS>
 __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnParams& p, const Sched& s,
                                               int ratio, int lane, uint64_t pol, const Ranges<CostQK>& rq, int& ready_unit)
 {
@@ -1005,7 +996,7 @@ __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnP
         cur.j = 0; ++cur.unit; --cur.left;
     }
     if (cur.left <= 0) return;
-    if (PART != kIssueCache && cur.unit != ready_unit) { wait_unit_ready(p, s, rq, cur.unit, lane); ready_unit = cur.unit; }
+    if (cur.unit != ready_unit) { wait_unit_ready(p, s, rq, cur.unit, lane); ready_unit = cur.unit; }
     if (lane == 0) {
         const int u = p.hchunks == 1 ? cur.unit : cur.unit / p.hchunks, hc = p.hchunks == 1 ? 0 : cur.unit % p.hchunks;
         uint8_t* dst = pp.prod();
@@ -1015,33 +1006,24 @@ __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnP
             constexpr int cb = kHalfChunks * Lay<VB>::kChunkBytes;    // codes of a stage-item
             const int mb = lay_meta_bytes(GS) / kParts;
             const uint8_t* blk = c.v_store + ((int64_t)u * c.v_cap_blocks + cur.j) * lay_block_bytes(VB, GS);
-            if (PART == kIssueAll) mbar_expect_tx(bar, (uint32_t)(cb + mb + G * kPartTokens * 2));
-            else if (PART == kIssueCache) mbar_expect_tx_only(bar, (uint32_t)(cb + mb));
-            else mbar_expect_tx(bar, (uint32_t)(G * kPartTokens * 2));
-            if (PART != kIssueLogits) {
-                if (kParts == 1) {
-                    bulk_g2s(dst, blk, (uint32_t)(cb + mb), bar, pol);    // codes and meta are contiguous: one copy
-                } else {
-                    bulk_g2s(dst, blk + cur.half * cb, cb, bar, pol);
-                    bulk_g2s(dst + cb, blk + kParts * cb + cur.half * mb, (uint32_t)mb, bar, pol);
-                }
+            mbar_expect_tx(bar, (uint32_t)(cb + mb + G * kPartTokens * 2));
+            if (kParts == 1) {
+                bulk_g2s(dst, blk, (uint32_t)(cb + mb), bar, pol);    // codes and meta are contiguous: one copy
+            } else {
+                bulk_g2s(dst, blk + cur.half * cb, cb, bar, pol);
+                bulk_g2s(dst + cb, blk + kParts * cb + cur.half * mb, (uint32_t)mb, bar, pol);
             }
-            if (PART != kIssueCache) {
-                const int uq0 = u * ratio + hc * G;
-                for (int h = 0; h < G; ++h)                           // the logits of the item's tokens (workspace rows)
-                    bulk_g2s(dst + cb + mb + h * kPartTokens * 2,
-                             p.w.lg + (int64_t)(uq0 + h) * p.w.ld + cur.j * kBlockTokens + cur.half * kPartTokens,
-                             kPartTokens * 2, bar, pol);
-            }
-        } else if (PART == kIssueLogits) {
-            mbar_arrive(bar);                                         // the window rows are on their way; their logits are read directly
+            const int uq0 = u * ratio + hc * G;
+            for (int h = 0; h < G; ++h)                               // the logits of the item's tokens (workspace rows)
+                bulk_g2s(dst + cb + mb + h * kPartTokens * 2,
+                         p.w.lg + (int64_t)(uq0 + h) * p.w.ld + cur.j * kBlockTokens + cur.half * kPartTokens,
+                         kPartTokens * 2, bar, pol);
         } else {
             const int i = cur.j - s.n_vb;
             int slot0, nt;
             if (i < s.vr1) { const int t0 = i * kResTile; slot0 = s.vhead + t0; nt = min(kResTile, s.seg1 - t0); }
             else { const int t0 = (i - s.vr1) * kResTile; slot0 = t0; nt = min(kResTile, s.L - s.seg1 - t0); }
-            if (PART == kIssueAll) mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
-            else mbar_expect_tx_only(bar, (uint32_t)(nt * kD * 2));
+            mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
             bulk_g2s(dst, c.v_res + ((int64_t)u * c.v_res_cap + slot0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
         }
     }
@@ -1100,14 +1082,6 @@ sv_kernel(const AttnParams p)
     Cursor cur;
     cur.unit = u_lo; cur.j = j_lo; cur.half = 0; cur.left = n_mine;
     int ready_unit = -1;                                                     // last unit whose q.K^T ranges are known to be complete
-#if KIVI_SV_PREFETCH
-    // The packed V blocks / window rows of this warp's first stages go in flight NOW, while the q.K^T kernel is still
-    // finishing elsewhere (this CTA got its SM when that SM's q.K^T CTA left): nothing in them is written by that kernel.
-    {
-        Pipe pq = pp; Cursor cq = cur;
-        for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS, kIssueCache>(pq, cq, p, s, ratio, lane, pol, rq_sh, ready_unit);
-    }
-#endif
     if (s.r + 1 == c.R) {                                                    // the step that completes the K window: flush it now
         const int n_slices = 4 * c.B * c.Hkv, n_workers = (int)rg.W;
         for (int sl = gw; sl < n_slices; sl += n_workers) k_flush_slice<KB>(p, s, sl >> 2, sl & 3, lane);
@@ -1149,8 +1123,7 @@ sv_kernel(const AttnParams p)
     // the few statistics words first, THEN the bulk copies: every warp of the grid issues its first stages at this very
     // moment (~29 MB in flight), and a small load queued behind them would be the last thing to arrive
     fetch_stats(unit);
-    for (int i = 0; i < p.spw; ++i)
-        sv_issue_next<VB, G, GS, KIVI_SV_PREFETCH ? kIssueLogits : kIssueAll>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
+    for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
     KIVI_TL(1, gw, 1);
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
     CommitIn pend_cin = {};
