@@ -1,5 +1,7 @@
 // Pipe-rate microbenchmark for the decode-attention design space (sm_100a): legacy mma.sync fp16 vs u8 vs e4m3,
 // fp8 conversions, LOP3 / PRMT.  One CTA per SM, W warps per CTA; cycles per warp instruction per sub-partition.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/ubench/pipes tools/ubench/pipes.cu && tools/ubench/pipes
+// Results on B200: profiles/r02_pipe_rates.txt (mma.sync with e4m3 operands is lowered by ptxas to F2FP unpacks + HMMA).
 #include <cstdio>
 #include <cstdint>
 #include <cuda_fp16.h>
