@@ -755,11 +755,8 @@ qk_kernel(const AttnParams p)
 
     __shared__ Ranges<CostQK> rg_sh;                                         // items of the whole job over the range owners
     const Sched s = make_sched(c);
-    if (tid == 0) {
-        for (int i = 0; i < n_stages; ++i) mbar_init(&full_all[i], 1);
-        mbar_fence_init();
-        rg_sh.init(p.n_units, s.n_kb, s.n_kr, p.nw_eff);
-    }
+    if (tid < n_stages) { mbar_init(&full_all[tid], 1); mbar_fence_init(); } // one stage barrier per thread, the work split beside them
+    if (tid == kThreads - 1) rg_sh.init(p.n_units, s.n_kb, s.n_kr, p.nw_eff);
     __syncthreads();                                                         // the only CTA barrier: mbarrier init, work split
     pdl_trigger();                                                           // the p.V kernel may start its prologue
 
@@ -1058,12 +1055,9 @@ sv_kernel(const AttnParams p)
     __shared__ Ranges<CostSV> rg_sh;                                         // this kernel's work split
     __shared__ Ranges<CostQK> rq_sh;                                         // the q.K^T kernel's (statistics slots per unit)
     const Sched s = make_sched(c);
-    if (tid == 0) {
-        for (int i = 0; i < n_stages; ++i) mbar_init(&full_all[i], 1);
-        mbar_fence_init();
-        rg_sh.init(p.n_units, s.n_vb, s.n_vr, p.nw_eff);
-        rq_sh.init(p.n_units, s.n_kb, s.n_kr, p.nw_eff);
-    }
+    if (tid < n_stages) { mbar_init(&full_all[tid], 1); mbar_fence_init(); } // one stage barrier per thread, the work splits beside them
+    if (tid == kThreads - 1) rg_sh.init(p.n_units, s.n_vb, s.n_vr, p.nw_eff);
+    if (tid == kThreads - 33) rq_sh.init(p.n_units, s.n_kb, s.n_kr, p.nw_eff);
     __syncthreads();                                                         // the only CTA barrier: mbarrier init, work splits
 
     const uint64_t pol = KIVI_EVICT_FIRST ? policy_evict_first() : policy_evict_last();
