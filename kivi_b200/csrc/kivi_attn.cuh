@@ -66,6 +66,24 @@ constexpr int kChunkUnroll = KIVI_UNROLL;
 #ifndef KIVI_UNIT_FLAGS
 #define KIVI_UNIT_FLAGS 0
 #endif
+// 1: the units' cache updates (V-token pack, window appends) are done by the q.K^T warps AFTER their ranges, one unit per
+// ticket of a device counter (a finished warp draws until none is left), instead of at the start of the p.V kernel, where they
+// sit on the critical path of 43 % of its warps (1024 units over 2368 warps: 96 % of the latest tenth of the p.V warps are
+// committing warps, +2.9 us each; profiles/r02_timeline_commit.txt).  Correct (GPU suite + memcheck pass) but MEASURED SLOWER:
+// too few q.K^T warps finish early enough, the draws run until 47.9 us instead of the grid ending at 45.6 us, and the p.V
+// kernel gains only 1.3 us of it back (cfg 2: 0.0955 vs 0.0923 ms per call, cfg 3 0.1312 vs 0.1283, B = 128 0.3296 vs 0.3249).
+#ifndef KIVI_COMMIT_IN_QK
+#define KIVI_COMMIT_IN_QK 0
+#endif
+#if KIVI_COMMIT_IN_QK && KIVI_UNIT_FLAGS
+#error "KIVI_COMMIT_IN_QK relies on the grid dependency between the two kernels (the ticket reset); KIVI_UNIT_FLAGS removes it"
+#endif
+#ifndef KIVI_PREFETCH_SV
+#define KIVI_PREFETCH_SV 0               // n > 0: a finished q.K^T warp requests the first n packed V items of "its" p.V range into L2
+#endif
+#ifndef KIVI_COMMIT_LATE
+#define KIVI_COMMIT_LATE 0               // 1: the early cache updates run after the warp's first stages are in flight instead of before the grid-dependency wait
+#endif
 
 namespace kivi {
 
@@ -79,6 +97,9 @@ int make_desc(const kivi_cache_t* k, CacheDesc* d);
 #endif
 constexpr int kCW = KIVI_CW;
 constexpr int kThreads = kCW * 32;
+#ifndef KIVI_MINB
+#define KIVI_MINB (KIVI_CW >= 16 ? 1 : 2)   // CTAs per SM the kernels are compiled for (register budget) and launched with
+#endif
 // A pipeline stage holds kHalfChunks of the 8 chunks (16 inner indices each) of a packed block: 8 = whole blocks
 // (one 6 KB bulk copy), 4 = half blocks.  Measured (tools/sweep_occupancy.sh, profiles/): half blocks allow 3 CTAs
 // per SM (24 warps) but cost +25 % instructions and more, smaller copies -> 175 us vs 140 us per cfg-2 layer.
@@ -118,6 +139,7 @@ struct Workspace {                     // carved from the caller's buffer (kivi_
     float* part; int part_cap;         // [n_units][part_cap][G][2][128] partial outputs (packed | window)
     int* count;                        // [n_units] arrivals of sv ranges; the last arriver resets it to 0
     int* ready;                        // [n_units] q.K^T ranges of the unit that have published logits + statistics (reset by the finaliser)
+    int* ticket;                       // [1] next unit whose cache update is up for grabs (q.K^T warps draw, the p.V kernel resets it to 0)
 };
 
 struct AttnParams {
@@ -740,7 +762,7 @@ __device__ __forceinline__ void qk_issue_next(Pipe& pp, Cursor& cur, const AttnP
 }
 
 template <int KB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, kCW >= 16 ? 1 : 2)
+__global__ void __launch_bounds__(kThreads, KIVI_MINB)
 qk_kernel(const AttnParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -961,6 +983,53 @@ qk_kernel(const AttnParams p)
         left -= n_here;
         if (j == s.ipu) { j = 0; ++unit; }
     }
+    KIVI_TL(0, gw, 2);
+#if KIVI_COMMIT_IN_QK && KIVI_EARLY_COMMIT
+    // The units' cache updates (models/llama_kivi.py:343-356 without the flush, :386-399): they read k_new / v_new / the oldest
+    // V window token and write only what no kernel of this step reads (the free ring slot, K window row r, token tv of the V
+    // store, whose probability the p.V block loop forces to zero), so any warp may do any unit at any time after the
+    // predecessor grid has completed.  A warp that has finished its range draws units from a device counter until none is
+    // left: the early finishers absorb the work in the time they would wait for the stragglers of the grid, and every unit is
+    // updated before the grid completes.  Which warp updates which unit does not change a single bit of the result.
+    {
+        const int nu = c.B * c.Hkv;
+        uint8_t* scratch = reinterpret_cast<uint8_t*>(qlin);                 // this warp's 512 G bytes: q is no longer needed
+        #pragma unroll 1
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(p.w.ticket, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= nu) break;
+            if (c.v_bits == 2) commit_unit<KB, 2>(p, s, t, lane, scratch, commit_fetch(p, s, t, lane));
+            else commit_unit<KB, 4>(p, s, t, lane, scratch, commit_fetch(p, s, t, lane));
+        }
+    }
+#endif
+#if KIVI_PREFETCH_SV
+    // This warp is done; its CTA (and the SM) stays until the slowest of its 16 warps is, and the p.V grid cannot start before
+    // the whole q.K^T grid has drained.  The first packed V items of the p.V range with the same index (the p.V kernel's own
+    // split, recomputed here) are requested into L2 now: HBM has spare bandwidth in this kernel's tail, and the p.V kernel's
+    // first stages -- ~29 MB requested by every warp at the same moment -- then come from L2.  A hint only: no result depends on it.
+    {
+        Ranges<CostSV> rs;
+        rs.init(p.n_units, s.n_vb, s.n_vr, p.nw_eff);
+        if (gw < (int)rs.W) {
+            int pu, pj;
+            rs.lo(gw, pu, pj);
+            #pragma unroll 1
+            for (int i = 0; i < KIVI_PREFETCH_SV && pu < p.n_units; ++i) {
+                if (pj < s.n_vb) {
+                    if (lane == 0) {
+                        const int u_ = p.hchunks == 1 ? pu : pu / p.hchunks;
+                        bulk_prefetch_l2(c.v_store + ((int64_t)u_ * c.v_cap_blocks + pj) * lay_block_bytes(c.v_bits, GS),
+                                         (uint32_t)lay_block_bytes(c.v_bits, GS));
+                    }
+                    ++pj;
+                } else { pj = 0; ++pu; }                                    // window items / new token: small, skipped
+            }
+        }
+    }
+#endif
     KIVI_TL(0, gw, 3);
 }
 
@@ -1039,7 +1108,7 @@ __device__ __forceinline__ float prob_f32(float x, float M, float S, float rS) {
 }
 
 template <int KB, int VB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, kCW >= 16 ? 1 : 2)
+__global__ void __launch_bounds__(kThreads, KIVI_MINB)
 sv_kernel(const AttnParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1051,6 +1120,7 @@ sv_kernel(const AttnParams p)
     uint8_t* ptr = smem + (((size_t)n_stages * (p.stage_bytes + 8) + 127) & ~(size_t)127);
     float* obuf = reinterpret_cast<float*>(ptr) + warp * (G * kD);             // per warp: [G][128] window-item outputs in channel order
     uint8_t* scratch = reinterpret_cast<uint8_t*>(obuf);                     // commit_unit scratch (128 bytes), same storage
+    (void)scratch;
 
     __shared__ Ranges<CostSV> rg_sh;                                         // this kernel's work split
     __shared__ Ranges<CostQK> rq_sh;                                         // the q.K^T kernel's (statistics slots per unit)
@@ -1080,18 +1150,28 @@ sv_kernel(const AttnParams p)
         const int n_slices = 4 * c.B * c.Hkv, n_workers = (int)rg.W;
         for (int sl = gw; sl < n_slices; sl += n_workers) k_flush_slice<KB>(p, s, sl >> 2, sl & 3, lane);
     }
-#if KIVI_EARLY_COMMIT
     // The units' cache updates (V-token pack, window appends) read k_new / v_new / the oldest window token and write only what
     // no kernel of this step reads: the free ring slot, window row r, and token tv of the V store (whose probability the block
-    // loop forces to zero).  They are done here, spread evenly over the warps, in the time this kernel waits for the q.K^T grid.
-    {
+    // loop forces to zero).  They are spread evenly over the warps.  KIVI_COMMIT_LATE = 0: before the grid-dependency wait
+    // (fills the time an early CTA waits for the q.K^T grid); 1: after the warp's first stages are in flight (their round
+    // trips -- dependent loads queued behind the ~29 MB of first-stage copies every warp issues at that moment -- then overlap
+    // the flight of the warp's own first block instead of delaying its issue: the p90 of "first stage issued" was 5 us behind
+    // the median in the per-warp timeline, and those late starters set the end of the kernel).
+#if !KIVI_COMMIT_IN_QK
+    auto commit_share = [&]() {
         const long long nu = (long long)c.B * c.Hkv, nwk = (long long)rg.W;
         const int u0 = (int)((gw * nu + nwk - 1) / nwk), u1 = (int)(((gw + 1) * nu + nwk - 1) / nwk);
         for (int uu = u0; uu < u1; ++uu) commit_unit<KB, VB>(p, s, uu, lane, scratch, commit_fetch(p, s, uu, lane));
-    }
+    };
+#endif
+#if KIVI_EARLY_COMMIT && !KIVI_COMMIT_LATE && !KIVI_COMMIT_IN_QK
+    commit_share();
 #endif
 #if !KIVI_UNIT_FLAGS
     pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
+#endif
+#if KIVI_COMMIT_IN_QK && KIVI_EARLY_COMMIT
+    if (gw == 0 && lane == 0) *p.w.ticket = 0;                               // every draw of the q.K^T grid has completed: ready for the next call
 #endif
 
     constexpr int NG = Cols<G, GS>::NG;
@@ -1119,6 +1199,9 @@ sv_kernel(const AttnParams p)
     fetch_stats(unit);
     for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
     KIVI_TL(1, gw, 1);
+#if KIVI_EARLY_COMMIT && KIVI_COMMIT_LATE && !KIVI_COMMIT_IN_QK
+    commit_share();
+#endif
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
     CommitIn pend_cin = {};
     // The last warp to arrive for a unit adds the records in range order, rounds, writes the output, updates the cache.
@@ -1381,7 +1464,7 @@ sv_kernel(const AttnParams p)
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxCtasPerSm = kCW >= 16 ? 1 : 2;
+constexpr int kMaxCtasPerSm = KIVI_MINB;
 
 // workspace carve-up (shared by kivi_decode_workspace_bytes and the launcher); negative = KIVI_ERR_* / -cudaError
 static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, int max_kv_len, void* base, Workspace* w)
@@ -1402,6 +1485,7 @@ static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, in
     const int64_t o_pt = take((int64_t)n_units * part_cap * G * 2 * kD * 4);
     const int64_t o_ct = take((int64_t)n_units * 4);
     const int64_t o_rd = take((int64_t)n_units * 4);
+    const int64_t o_tk = take(4);
     if (w) {
         uint8_t* b = (uint8_t*)base;
         w->lg = (__half*)(b + o_lg); w->ld = ld;
@@ -1409,6 +1493,7 @@ static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, in
         w->part = (float*)(b + o_pt); w->part_cap = part_cap;
         w->count = (int*)(b + o_ct);
         w->ready = (int*)(b + o_rd);
+        w->ticket = (int*)(b + o_tk);
     }
     return off;
 }

@@ -39,17 +39,25 @@ assert fn(buf.ctypes.data) == 0
 os.makedirs('gpurun_out', exist_ok=True)
 np.save(os.environ.get('KIVI_TL_OUT', 'gpurun_out/timeline.npy'), buf)
 t0 = buf[0][:, 0][buf[0][:, 0] > 0].min()
-for kname, kk, cols in (("qk", 0, (0, 1, 3)), ("sv", 1, (0, 1, 2, 3))):
+for kname, kk, cols in (("qk", 0, (0, 1, 2, 3)), ("sv", 1, (0, 1, 2, 3))):
     a = buf[kk]
     act = a[:, 0] > 0
     rel = (a[act][:, :4].astype(np.float64) - float(t0)) / 1e3
-    names = {0: "entry", 1: "first q/stats issued", 2: "blocks done", 3: "exit"}
+    names = {0: "entry", 1: "first q/stats issued", 2: "blocks done", 3: "exit"}   # qk: exit - blocks done = the ticketed cache updates
     print(f"{kname}: {act.sum()} warps")
     for c in cols:
         x = rel[:, c]
         print(f"   {names[c]:22s} min {x.min():7.2f}  p10 {np.percentile(x, 10):7.2f}  median {np.median(x):7.2f}  p90 {np.percentile(x, 90):7.2f}  max {x.max():7.2f} us")
     d = rel[:, cols[-1]] - rel[:, 0]
     print(f"   warp lifetime          min {d.min():7.2f}  median {np.median(d):7.2f}  max {d.max():7.2f} us")
+
+# ---- where the spread of the exit times sits: between CTAs (SM position) or between the warps of a CTA
+for kname, kk in (("qk", 0), ("sv", 1)):
+    a = buf[kk]
+    n = int((a[:, 0] > 0).sum()) // 16 * 16
+    ex = ((a[:n, 3].astype(np.float64) - float(t0)) / 1e3).reshape(-1, 16)
+    print(f"{kname}: exit std {ex.std():.2f} us = between CTA means {ex.mean(1).std():.2f} / within a CTA {ex.std(1).mean():.2f}; "
+          f"latest warp of a CTA: median {np.median(ex.max(1)):.2f}, max {ex.max():.2f}; CTA means max {ex.mean(1).max():.2f} us")
 
 # ---- cost regression: warp lifetime against the composition of its range (the split the library itself computes)
 def _composition(kernel, n_units, n_b, n_w, w_cap):
