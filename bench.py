@@ -244,8 +244,9 @@ def attention_roofline(model, cache, step_ms):
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
     G = 4 if (H // Hkv) % 4 == 0 else (2 if (H // Hkv) % 2 == 0 else 1)
-    roof = {"kernel": f"kivi_decode_attention_f16 = kivi::qk_kernel<{cache.k_bits},{G},{cache.group_size}> + "
-                      f"kivi::sv_kernel<{cache.k_bits},{cache.v_bits},{G},{cache.group_size}> (q.Kq^T + window + softmax "
+    cw = 12 if (cache.k_bits == 4 and G == 4) else 16                         # warps per CTA of the instantiation (kivi_attn.cuh: WarpsPerCta)
+    roof = {"kernel": f"kivi_decode_attention_f16 = kivi::qk_kernel<{cache.k_bits},{G},{cache.group_size},{cw}> + "
+                      f"kivi::sv_kernel<{cache.k_bits},{cache.v_bits},{G},{cache.group_size},{cw}> (q.Kq^T + window + softmax "
                       "statistics | normalise + p.Vq + window + output + cache update), timed as one call",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,

@@ -96,10 +96,18 @@ int make_desc(const kivi_cache_t* k, CacheDesc* d);
 #define KIVI_CW 16
 #endif
 constexpr int kCW = KIVI_CW;
-constexpr int kThreads = kCW * 32;
 #ifndef KIVI_MINB
 #define KIVI_MINB (KIVI_CW >= 16 ? 1 : 2)   // CTAs per SM the kernels are compiled for (register budget) and launched with
 #endif
+// The 4-bit K kernels that serve four query heads per KV head run 12 warps per CTA: at 16 warps their accumulators and the
+// four heads' B fragments spill (128 registers), at 12 they have 170 and the 4-bit block loop needs fewer warps to cover its
+// latencies (half the unpack instructions per byte).  Measured, one B200, per call (profiles/r02_warps_per_cta.txt):
+// cfg 4 (K4V4 g64, G = 4) 0.1325 vs 0.1410 ms, K4V4 g128 G = 4 0.0798 vs 0.0857 ms; G = 1 equal, G = 2 -1 %; 14 / 11 / 10
+// warps slower; the 2-bit kernels lose 5 - 11 % at 12 warps (cfg 2, cfg 3) and stay at 16.
+#ifndef KIVI_CW_K4G4
+#define KIVI_CW_K4G4 12
+#endif
+template <int KB, int G> struct WarpsPerCta { static constexpr int k = (KB == 4 && G == 4 && KIVI_CW >= 16) ? KIVI_CW_K4G4 : kCW; };
 // A pipeline stage holds kHalfChunks of the 8 chunks (16 inner indices each) of a packed block: 8 = whole blocks
 // (one 6 KB bulk copy), 4 = half blocks.  Measured (tools/sweep_occupancy.sh, profiles/): half blocks allow 3 CTAs
 // per SM (24 warps) but cost +25 % instructions and more, smaller copies -> 175 us vs 140 us per cfg-2 layer.
@@ -761,10 +769,11 @@ __device__ __forceinline__ void qk_issue_next(Pipe& pp, Cursor& cur, const AttnP
     if (++cur.j == s.ipu) { cur.j = 0; ++cur.unit; }
 }
 
-template <int KB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, KIVI_MINB)
+template <int KB, int G, int GS, int CW>
+__global__ void __launch_bounds__(CW * 32, KIVI_MINB)
 qk_kernel(const AttnParams p)
 {
+    constexpr int kCW = CW, kThreads = CW * 32;                              // warps / threads of this instantiation
     extern __shared__ __align__(128) uint8_t smem[];
     const CacheDesc& c = p.c;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1107,10 +1116,11 @@ __device__ __forceinline__ float prob_f32(float x, float M, float S, float rS) {
     return fmaf(fmaf(-q, S, e), rS, q);     // one Newton step on the quotient = the correctly rounded e / S
 }
 
-template <int KB, int VB, int G, int GS>
-__global__ void __launch_bounds__(kThreads, KIVI_MINB)
+template <int KB, int VB, int G, int GS, int CW>
+__global__ void __launch_bounds__(CW * 32, KIVI_MINB)
 sv_kernel(const AttnParams p)
 {
+    constexpr int kCW = CW, kThreads = CW * 32;                              // warps / threads of this instantiation
     extern __shared__ __align__(128) uint8_t smem[];
     const CacheDesc& c = p.c;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1475,7 +1485,7 @@ static inline int64_t carve_workspace(const CacheDesc& c, int n_units, int G, in
     const int64_t rows = (int64_t)c.B * c.H;
     const int64_t ld = ((int64_t)max_kv_len + 16 + 127) / 128 * 128 + 128;
     const int bpu_max = cdiv(max_kv_len, kBlockTokens) + cdiv(c.R + 1, kResTile) + 4;
-    const int warps = di.num_sms * kMaxCtasPerSm * kCW;
+    const int warps = di.num_sms * kMaxCtasPerSm * kCW;                     // the largest CTA any instantiation launches
     const int part_cap = min(bpu_max, cdiv(warps, n_units) + 2);
     int64_t off = 0;
     auto take = [&](int64_t bytes) { const int64_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -1506,6 +1516,7 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     int rc = device_info(&di);
     if (rc) return rc;
     const Tuning& tn = tuning();
+    constexpr int kCW = WarpsPerCta<KB, G>::k, kThreads = kCW * 32;          // (shadows the global default)
     const int max_smem = di.max_smem_optin - 1024;                           // room for the kernels' static shared memory (work split, 128 B)
     const int half_k = kHalfChunks * Lay<KB>::kChunkBytes + lay_meta_bytes(c.g) / kParts;
     const int half_v = kHalfChunks * Lay<VB>::kChunkBytes + lay_meta_bytes(c.g) / kParts + G * kPartTokens * 2;
@@ -1526,8 +1537,8 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     if (tn.stages_per_warp >= 1 && tn.stages_per_warp <= p.spw) p.spw = tn.stages_per_warp;
     if (p.spw < 1) return KIVI_ERR_CAPACITY;
     const size_t smem = (size_t)kCW * p.spw * p.stage_bytes + fixed;
-    auto kqk = qk_kernel<KB, G, GS>;
-    auto ksv = sv_kernel<KB, VB, G, GS>;
+    auto kqk = qk_kernel<KB, G, GS, kCW>;
+    auto ksv = sv_kernel<KB, VB, G, GS, kCW>;
     static std::atomic<unsigned long long> optin_qk{0}, optin_sv{0};        // per kernel instantiation, one bit per device
     rc = ensure_dynamic_smem(kqk, max_smem, di.ordinal, optin_qk); if (rc) return rc;
     rc = ensure_dynamic_smem(ksv, max_smem, di.ordinal, optin_sv); if (rc) return rc;

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "kivi_b200", "csrc", "libkivi_b200.so")
 WATCH = ["UBLKCP", "SYNCS", "HMMA", "LDSM", "LDGSTS", "LOP3", "PRMT", "SHF", "IMAD", "MUFU", "LDS", "STS", "LDG", "STG", "ATOMG", "RED",
          "LDL", "STL", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "BAR", "ERRBAR", "CCTL"]
-KERNELS = [r"qk_kernel<2, 1, 32>", r"sv_kernel<2, 2, 1, 32>", r"qk_kernel<2, 4, 32>", r"sv_kernel<2, 2, 4, 32>",
-           r"qk_kernel<4, 4, 64>", r"sv_kernel<4, 4, 4, 64>", r"bgm::wide_kernel<2, 1, 32>", r"bgm::tall_kernel<2, 1, 32>",
+KERNELS = [r"qk_kernel<2, 1, 32, 16>", r"sv_kernel<2, 2, 1, 32, 16>", r"qk_kernel<2, 4, 32, 16>", r"sv_kernel<2, 2, 4, 32, 16>",
+           r"qk_kernel<4, 4, 64, 12>", r"sv_kernel<4, 4, 4, 64, 12>", r"bgm::wide_kernel<2, 1, 32>", r"bgm::tall_kernel<2, 1, 32>",
            r"pack_lastdim_kernel<2", r"block_prefill_kernel<2, true>"]
 
 def main():
