@@ -81,6 +81,42 @@ constexpr int kChunkUnroll = KIVI_UNROLL;
 #ifndef KIVI_PREFETCH_SV
 #define KIVI_PREFETCH_SV 0               // n > 0: a finished q.K^T warp requests the first n packed V items of "its" p.V range into L2
 #endif
+// Latency fixes read off the ncu source counters of the cfg-2 call (profiles/r02_latency_fixes.txt); A/B per shape, graph-timed:
+//   KIVI_Q_FIRST         q.K^T issues ONE stage, fetches q, then the other stages (0: all stages first).  G = 1: -1.0 % per call
+//                        (cfg 2); G = 4: 0 ... +0.7 % (cfg 3 / cfg 4) -> applied to the G = 1 kernels only.
+//   KIVI_WIN_LOGITS_BULK the logits of a V window item travel with its bulk-copy group instead of a dependent global load.
+//                        G = 1: -0.4 % (cfg 2); G = 4 (4 extra copies per item): +0.3 ... +0.5 % -> G = 1 only.
+//   KIVI_REL_ARRIVE      the p.V arrival as a release, the acquire only in the last arriver: +0.4 % (cfg 2) / -0.4 % (cfg 3),
+//                        i.e. nothing: off.
+// 1: the inputs of a warp's cache update travel as the first item of its stage queue (see the p.V kernel).  The first stages
+// are then issued by all warps within 0.5 us of each other (p90 of "first stage issued": 47.6 instead of 54 us), but the call
+// gets SLOWER (cfg 2 0.0939 vs 0.0924 ms, B = 128 0.3264 vs 0.3218, same box): the committing warps start with one packed block
+// in flight instead of two.  Off.
+#ifndef KIVI_COMMIT_ASYNC
+#define KIVI_COMMIT_ASYNC 0
+#endif
+#ifndef KIVI_Q_FIRST
+#define KIVI_Q_FIRST 1
+#endif
+#ifndef KIVI_REL_ARRIVE
+#define KIVI_REL_ARRIVE 0
+#endif
+#ifndef KIVI_WIN_LOGITS_BULK
+#define KIVI_WIN_LOGITS_BULK 1
+#endif
+// The kernel parameters are __grid_constant__: the noinline cache-update callees (commit_unit, k_flush_slice) take `const
+// AttnParams&`, and without the qualifier every thread of the p.V kernel first copied the 350-byte struct to local memory --
+// 26 MB of local stores at the very moment the grid starts (ncu: STL.128 rows with lg_throttle stalls, 3 % of the kernel's warp
+// time; stack frame 352 -> 112 bytes).  -3.0 % per cfg-2 call (0.0923 -> 0.0896 ms).  -DKIVI_GRID_CONSTANT=0 for the A/B.
+#ifndef KIVI_GRID_CONSTANT
+#define KIVI_GRID_CONSTANT 1
+#endif
+#if KIVI_GRID_CONSTANT
+#define KIVI_PARAM_QUAL __grid_constant__
+#else
+#define KIVI_PARAM_QUAL
+#endif
+template <int G> struct Lat { static constexpr bool q_first = KIVI_Q_FIRST && G == 1, win_bulk = KIVI_WIN_LOGITS_BULK && G == 1; };
 #ifndef KIVI_COMMIT_LATE
 #define KIVI_COMMIT_LATE 0               // 1: the early cache updates run after the warp's first stages are in flight instead of before the grid-dependency wait
 #endif
@@ -771,7 +807,7 @@ __device__ __forceinline__ void qk_issue_next(Pipe& pp, Cursor& cur, const AttnP
 
 template <int KB, int G, int GS, int CW>
 __global__ void __launch_bounds__(CW * 32, KIVI_MINB)
-qk_kernel(const AttnParams p)
+qk_kernel(const KIVI_PARAM_QUAL AttnParams p)
 {
     constexpr int kCW = CW, kThreads = CW * 32;                              // warps / threads of this instantiation
     extern __shared__ __align__(128) uint8_t smem[];
@@ -806,7 +842,11 @@ qk_kernel(const AttnParams p)
     pp.init(smem + (size_t)warp * p.spw * p.stage_bytes, full_all + warp * p.spw, p.spw, p.stage_bytes);
     Cursor cur;
     cur.unit = u_lo; cur.j = j_lo; cur.half = 0; cur.left = n_mine;
-    for (int i = 0; i < p.spw; ++i) qk_issue_next<KB, GS>(pp, cur, p, s, lane, pol);
+    // ONE stage goes out before the grid-dependency wait (the packed cache does not depend on the predecessor); the others
+    // follow the q fetch below: issued after all of a warp's first stages, the few q words queue behind the ~29 MB every warp
+    // of the grid requests at this moment and arrive last -- 6.9 % of the kernel's warp time sat on their first use
+    // (ncu source counters, profiles/r02_attention_ncu_summary.txt).
+    for (int i = 0; i < (Lat<G>::q_first ? 1 : p.spw); ++i) qk_issue_next<KB, GS>(pp, cur, p, s, lane, pol);
 
     constexpr int NG = Cols<G, GS>::NG;
     const int ratio = c.H / c.Hkv;
@@ -828,6 +868,8 @@ qk_kernel(const AttnParams p)
     };
     pdl_wait();                                                              // q / k_new come from the previous kernel of the stream
     fetch_q(unit);
+    if (Lat<G>::q_first)
+        for (int i = 1; i < p.spw; ++i) qk_issue_next<KB, GS>(pp, cur, p, s, lane, pol);
     KIVI_TL(0, gw, 1);
     #pragma unroll 1
     while (left > 0) {
@@ -1098,8 +1140,21 @@ __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnP
             int slot0, nt;
             if (i < s.vr1) { const int t0 = i * kResTile; slot0 = s.vhead + t0; nt = min(kResTile, s.seg1 - t0); }
             else { const int t0 = (i - s.vr1) * kResTile; slot0 = t0; nt = min(kResTile, s.L - s.seg1 - t0); }
-            mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
-            bulk_g2s(dst, c.v_res + ((int64_t)u * c.v_res_cap + slot0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
+            if (Lat<G>::win_bulk && p.spw >= 2) {
+                // + the item's logits: 48 bytes from the 16-byte boundary at or below logit (tv + l0) of every head's workspace
+                // row (rows are 256-byte aligned and padded by 128 entries), behind the 16 window rows of the stage
+                mbar_expect_tx(bar, (uint32_t)(nt * kD * 2 + G * 48));
+                bulk_g2s(dst, c.v_res + ((int64_t)u * c.v_res_cap + slot0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
+                const int l0 = i < s.vr1 ? i * kResTile : s.seg1 + (i - s.vr1) * kResTile;
+                const int uq0 = u * ratio + hc * G;
+                for (int h = 0; h < G; ++h) {
+                    const int64_t e0 = ((int64_t)(uq0 + h) * p.w.ld + s.tv + l0) & ~(int64_t)7;
+                    bulk_g2s(dst + kResBytes + h * 64, p.w.lg + e0, 48u, bar, pol);
+                }
+            } else {
+                mbar_expect_tx(bar, (uint32_t)(nt * kD * 2));
+                bulk_g2s(dst, c.v_res + ((int64_t)u * c.v_res_cap + slot0) * kD, (uint32_t)(nt * kD * 2), bar, pol);
+            }
         }
     }
     pp.push();
@@ -1118,7 +1173,7 @@ __device__ __forceinline__ float prob_f32(float x, float M, float S, float rS) {
 
 template <int KB, int VB, int G, int GS, int CW>
 __global__ void __launch_bounds__(CW * 32, KIVI_MINB)
-sv_kernel(const AttnParams p)
+sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
 {
     constexpr int kCW = CW, kThreads = CW * 32;                              // warps / threads of this instantiation
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1175,7 +1230,11 @@ sv_kernel(const AttnParams p)
     };
 #endif
 #if KIVI_EARLY_COMMIT && !KIVI_COMMIT_LATE && !KIVI_COMMIT_IN_QK
+#if KIVI_COMMIT_ASYNC
+    if (p.spw < 2) commit_share();                                           // one stage per warp: no room for the inputs to travel in
+#else
     commit_share();
+#endif
 #endif
 #if !KIVI_UNIT_FLAGS
     pdl_wait();                                                              // logits and statistics come from the q.K^T kernel
@@ -1207,10 +1266,49 @@ sv_kernel(const AttnParams p)
     // the few statistics words first, THEN the bulk copies: every warp of the grid issues its first stages at this very
     // moment (~29 MB in flight), and a small load queued behind them would be the last thing to arrive
     fetch_stats(unit);
+#if KIVI_COMMIT_ASYNC && KIVI_EARLY_COMMIT && !KIVI_COMMIT_LATE && !KIVI_COMMIT_IN_QK
+    // The inputs of this warp's (first) cache update -- the v_new row, the k_new row, the oldest V window row: 3 x 256 bytes --
+    // travel as the FIRST item of the warp's stage queue and land together with its first packed block; the update itself is
+    // ~250 instructions.  Fetched with ordinary loads, the same words queued behind the ~29 MB of first-stage copies all warps
+    // issue at this moment: +2.9 us on the 43 % of the warps that have a unit to update, 96 % of the latest tenth of the grid
+    // (profiles/r02_timeline_commit.txt).
+    const long long cnu = (long long)c.B * c.Hkv, cnw = (long long)rg.W;
+    const int cu0 = (int)((gw * cnu + cnw - 1) / cnw), cu1 = (int)(((gw + 1) * cnu + cnw - 1) / cnw);
+    const bool commit_async = p.spw >= 2 && cu1 > cu0;
+    if (commit_async) {
+        if (lane == 0) {
+            uint8_t* dst = pp.prod();
+            uint64_t* bar = pp.prod_bar();
+            const bool vq = s.L + 1 > c.R;                                   // the window is full: its oldest token gets packed
+            mbar_expect_tx(bar, vq ? 768u : 512u);
+            bulk_g2s_plain(dst, p.v_new + (int64_t)cu0 * kD, 256u, bar);
+            bulk_g2s_plain(dst + 256, p.k_new + (int64_t)cu0 * kD, 256u, bar);
+            if (vq) bulk_g2s_plain(dst + 512, c.v_res + ((int64_t)cu0 * c.v_res_cap + s.vhead) * kD, 256u, bar);
+        }
+        pp.push();
+    }
+    for (int i = commit_async ? 1 : 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
+    KIVI_TL(1, gw, 1);
+    if (commit_async) {
+        pp.wait();
+        const uint8_t* st = pp.cons();
+        CommitIn in;
+        in.vnew4 = make_uint4(0u, 0u, 0u, 0u); in.knew4 = in.vnew4; in.vold = make_uint2(0u, 0u);
+        if (lane < kD / 8) in.vnew4 = reinterpret_cast<const uint4*>(st)[lane];
+        if (lane >= 16) in.knew4 = reinterpret_cast<const uint4*>(st + 256)[lane - 16];
+        if (s.L + 1 > c.R) in.vold = *reinterpret_cast<const uint2*>(st + 512 + 2 * (win_off(s.vhead, lane * 4) - s.vhead * kD));
+        __syncwarp();
+        pp.pop();
+        sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);     // the freed stage takes the next item at once
+        commit_unit<KB, VB>(p, s, cu0, lane, scratch, in);
+        for (int uu = cu0 + 1; uu < cu1; ++uu) commit_unit<KB, VB>(p, s, uu, lane, scratch, commit_fetch(p, s, uu, lane));
+    }
+#else
     for (int i = 0; i < p.spw; ++i) sv_issue_next<VB, G, GS>(pp, cur, p, s, ratio, lane, pol, rq, ready_unit);
     KIVI_TL(1, gw, 1);
 #if KIVI_EARLY_COMMIT && KIVI_COMMIT_LATE && !KIVI_COMMIT_IN_QK
     commit_share();
+#endif
 #endif
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
     CommitIn pend_cin = {};
@@ -1218,7 +1316,10 @@ sv_kernel(const AttnParams p)
     auto finish_unit = [&](int un, int nparts, const CommitIn& cin) {
         const int u = p.hchunks == 1 ? un : un / p.hchunks, hc = p.hchunks == 1 ? 0 : un % p.hchunks;
         const int uq0 = u * ratio + hc * G;
-        __syncwarp();                                                        // lane 0's acq_rel arrival covers the other lanes' reads
+#if KIVI_REL_ARRIVE
+        if (nparts > 1 && lane == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // the last arriver acquires: the counter value it read (relaxed) + this fence
+#endif
+        __syncwarp();                                                        // lane 0's acquire covers the other lanes' reads
         if (nparts > 1 && lane == 0) p.w.count[un] = 0;
 #if KIVI_UNIT_FLAGS
         if (lane == 0) p.w.ready[un] = 0;                                    // every p.V range of the unit has long passed its acquire
@@ -1360,12 +1461,21 @@ sv_kernel(const AttnParams p)
                 if (i < s.vr1) { l0 = i * kResTile; nt = min(kResTile, s.seg1 - l0); slot0 = s.vhead + l0; }
                 else { const int tt0 = (i - s.vr1) * kResTile; l0 = s.seg1 + tt0; nt = min(kResTile, s.L - s.seg1 - tt0); slot0 = tt0; }
                 // the item's probabilities: lane t < nt computes token tv + l0 + t
+                const bool win_bulk = Lat<G>::win_bulk && p.spw >= 2;        // (one stage per warp: nothing is prefetched, measured slower)
+                if (win_bulk) pp.wait();                                     // the logits arrive with the window rows
+                uint8_t* st = pp.cons();
                 float pl[G];
                 #pragma unroll
                 for (int h = 0; h < G; ++h) {
                     pl[h] = 0.f;
                     if (lane < nt) {
-                        const float x = __half2float(__ldcg(p.w.lg + (int64_t)(uq0 + h) * p.w.ld + s.tv + l0 + lane));
+                        float x;
+                        if (win_bulk) {
+                            const int off = (int)(((int64_t)(uq0 + h) * p.w.ld + s.tv + l0) & 7);
+                            x = __half2float(reinterpret_cast<const __half*>(st + kResBytes + h * 64)[off + lane]);
+                        } else {
+                            x = __half2float(__ldcg(p.w.lg + (int64_t)(uq0 + h) * p.w.ld + s.tv + l0 + lane));
+                        }
                         const __half pr = __float2half_rn(prob_f32(x, M[h], S[h], rS[h]));
                         if (p.dbg_probs) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + s.tv + l0 + lane] = pr;
                         pl[h] = __half2float(pr);
@@ -1379,8 +1489,7 @@ sv_kernel(const AttnParams p)
                     const float p2 = __shfl_sync(0xffffffffu, pl[h], 2 * t4 + 8), p3 = __shfl_sync(0xffffffffu, pl[h], 2 * t4 + 9);
                     if (g8 == h) { b0 = h2_as_u32(__floats2half2_rn(p0, p1)); b1 = h2_as_u32(__floats2half2_rn(p2, p3)); }
                 }
-                pp.wait();
-                uint8_t* st = pp.cons();
+                if (!win_bulk) pp.wait();
                 if (nt < kResTile) {                                         // rows past the item hold stale bytes (maybe NaN patterns)
                     for (int idx = lane; idx < (kResTile - nt) * 16; idx += 32)
                         *reinterpret_cast<uint4*>(st + nt * 256 + idx * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -1457,8 +1566,15 @@ sv_kernel(const AttnParams p)
         // done, so its round trip to L2 is off the critical path
         __syncwarp();
         if (nparts > 1) {
-            if (lane == 0)
+            if (lane == 0) {
+#if KIVI_REL_ARRIVE
+                // release only: the acquire half (an L1 invalidation waiting on the atomic's round trip, 2 % of the kernel's
+                // warp time over 3328 arrivals) is needed by the ONE warp that turns out to be last, and is done there
+                asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + unit) : "memory");
+#else
                 asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + unit) : "memory");
+#endif
+            }
             pend_unit = unit; pend_nparts = nparts;
         } else {
             finish_unit(unit, 1, pend_cin);                                  // the whole unit was this warp's
@@ -1520,7 +1636,7 @@ static int launch_attention(AttnParams& p, bool overlap_prologue, cudaStream_t s
     const int max_smem = di.max_smem_optin - 1024;                           // room for the kernels' static shared memory (work split, 128 B)
     const int half_k = kHalfChunks * Lay<KB>::kChunkBytes + lay_meta_bytes(c.g) / kParts;
     const int half_v = kHalfChunks * Lay<VB>::kChunkBytes + lay_meta_bytes(c.g) / kParts + G * kPartTokens * 2;
-    const int stage = max(max(half_k, half_v), kResBytes);
+    const int stage = max(max(half_k, half_v), kResBytes + G * 64);           // a window item: 16 rows + 48 B of logits per head
     p.stage_bytes = (stage + 127) / 128 * 128;
     const int fixed = 512 + kCW * G * (32 * 8 + kD * 4);                     // barriers + per-warp q buffers (qk) / window outputs (sv)
     int ctas = kMaxCtasPerSm;                                                // the kernels' __launch_bounds__
