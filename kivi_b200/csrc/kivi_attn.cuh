@@ -95,6 +95,13 @@ constexpr int kChunkUnroll = KIVI_UNROLL;
 #ifndef KIVI_COMMIT_ASYNC
 #define KIVI_COMMIT_ASYNC 0
 #endif
+// 1: a p.V arrival that is followed by another visit of the warp is issued after that visit's first item, when the record
+// stores have landed and the release fence returns at once (the fence + atomic + L1 invalidation of an arrival are 7.4 % of the
+// kernel's warp time).  Only 29 % of the arrivals have a visit behind them; MEASURED SLOWER: cfg 2 0.0894 vs 0.0887 ms, B = 128
+// 0.3177 vs 0.3153 (the test in the item loop costs more than the hidden fences save).  Off.
+#ifndef KIVI_DEFER_ARRIVE
+#define KIVI_DEFER_ARRIVE 0
+#endif
 #ifndef KIVI_Q_FIRST
 #define KIVI_Q_FIRST 1
 #endif
@@ -1311,6 +1318,21 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
 #endif
 #endif
     int pend_unit = -1, pend_old = 0, pend_nparts = 0;                       // arrival whose counter value is still in flight
+    constexpr bool kDefer = KIVI_DEFER_ARRIVE && G == 1;                     // (the G = 4 kernels have no registers to spare)
+    int arr_unit = -1, arr_nparts = 0;                                       // record written, arrival not yet issued
+    auto do_arrive = [&](int un, int np) {
+        __syncwarp();
+        if (lane == 0) {
+#if KIVI_REL_ARRIVE
+            // release only: the acquire half (an L1 invalidation waiting on the atomic's round trip, 2 % of the kernel's
+            // warp time over 3328 arrivals) is needed by the ONE warp that turns out to be last, and is done there
+            asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + un) : "memory");
+#else
+            asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + un) : "memory");
+#endif
+        }
+        pend_unit = un; pend_nparts = np;
+    };
     CommitIn pend_cin = {};
     // The last warp to arrive for a unit adds the records in range order, rounds, writes the output, updates the cache.
     auto finish_unit = [&](int un, int nparts, const CommitIn& cin) {
@@ -1541,6 +1563,7 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
                     orr[h][2] = fmaf(pr, v23.x, orr[h][2]); orr[h][3] = fmaf(pr, v23.y, orr[h][3]);
                 }
             }
+            if (kDefer && arr_unit >= 0) { do_arrive(arr_unit, arr_nparts); arr_unit = -1; }   // the previous unit's arrival, one item later
         }
 
         // ---- this warp's partial record of the unit: [G][packed | window][128]
@@ -1564,19 +1587,13 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
         // arrive: the records of all lanes happen-before lane 0's release (__syncwarp), and its acquire makes the records of
         // the earlier arrivals visible to a last arriver; the counter's old value is not needed before the next unit is
         // done, so its round trip to L2 is off the critical path
-        __syncwarp();
         if (nparts > 1) {
-            if (lane == 0) {
-#if KIVI_REL_ARRIVE
-                // release only: the acquire half (an L1 invalidation waiting on the atomic's round trip, 2 % of the kernel's
-                // warp time over 3328 arrivals) is needed by the ONE warp that turns out to be last, and is done there
-                asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + unit) : "memory");
-#else
-                asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.w.count + unit) : "memory");
-#endif
-            }
-            pend_unit = unit; pend_nparts = nparts;
+            // another visit follows: the arrival waits until its first item is done -- by then the record stores above have
+            // landed and the release fence (7 % of the kernel's warp time when it follows the stores directly) returns at once
+            if (kDefer && left > n_here) { arr_unit = unit; arr_nparts = nparts; }
+            else do_arrive(unit, nparts);
         } else {
+            __syncwarp();
             finish_unit(unit, 1, pend_cin);                                  // the whole unit was this warp's
         }
         left -= n_here;
