@@ -757,6 +757,23 @@ struct Cursor {                         // (unit, pseudo-block, half) position o
     int unit, j, half, left;            // left = pseudo-blocks remaining in the range (including j)
 };
 
+// exp(x - m) with the subtraction folded into the multiply: ex2.approx(fma(x, log2 e, nml)), nml = -m * log2 e (one FFMA + MUFU)
+#ifndef KIVI_EXP_FMA
+#define KIVI_EXP_FMA 1
+#endif
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float fast_exp_sub(float x, float m, float nml) {
+#if KIVI_EXP_FMA
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(x, kLog2e, nml)));
+    (void)m;
+    return y;
+#else
+    (void)nml;
+    return fast_exp(x - m);
+#endif
+}
+
 // online softmax statistics: fold the values x[0..n) (any of them may be -inf = "no value") into (m, s)
 template <int N_>
 __device__ __forceinline__ void fold_stats(float& m, float& s, const float (&x)[N_]) {
@@ -765,8 +782,9 @@ __device__ __forceinline__ void fold_stats(float& m, float& s, const float (&x)[
     for (int e = 0; e < N_; ++e) mn = fmaxf(mn, x[e]);
     if (mn != -INFINITY) {
         float acc = s * fast_exp(m - mn);                 // m == -inf -> s * 0
+        const float nml = -mn * kLog2e;
         #pragma unroll
-        for (int e = 0; e < N_; ++e) acc += fast_exp(x[e] - mn);
+        for (int e = 0; e < N_; ++e) acc += fast_exp_sub(x[e], mn, nml);     // x = -inf ("no value") -> 0
         m = mn; s = acc;
     }
 }
@@ -1172,8 +1190,8 @@ __device__ __forceinline__ void sv_issue_next(Pipe& pp, Cursor& cur, const AttnP
 }
 
 // fp16 probability of a scaled logit: fp16(exp(x - M) / S)   (models/llama_kivi.py:375); rS = 1 / S
-__device__ __forceinline__ float prob_f32(float x, float M, float S, float rS) {
-    const float e = fast_exp(x - M);
+__device__ __forceinline__ float prob_f32(float x, float M, float nMl, float S, float rS) {
+    const float e = fast_exp_sub(x, M, nMl);
     const float q = e * rS;
     return fmaf(fmaf(-q, S, e), rS, q);     // one Newton step on the quotient = the correctly rounded e / S
 }
@@ -1399,7 +1417,7 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
 
         // ---- (M, S) of every head of the unit from the statistics slots of the qk ranges (identical in every warp);
         // the slots were fetched one unit ahead
-        float M[G], S[G], rS[G];
+        float M[G], S[G], rS[G], nMl[G];
         #pragma unroll
         for (int h = 0; h < G; ++h) {
             float mx = sn[h].x, sm = sn[h].y;
@@ -1411,6 +1429,7 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
                 mx = mn;
             }
             warp_max_sum(mx, sm, M[h], S[h]);
+            nMl[h] = -M[h] * kLog2e;
             rS[h] = __frcp_rn(S[h]);
         }
         if (left > n_here) fetch_stats(unit + 1);                            // the range continues into the next unit
@@ -1452,7 +1471,7 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
                         for (int e = 0; e < kPartTokens / 64; ++e) {         // 2 tokens per lane and pass
                             const int tt = (e * 32 + lane) * 2;
                             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(prob + h * kPartTokens + tt));
-                            __half2 pr = __floats2half2_rn(prob_f32(f.x, M[h], S[h], rS[h]), prob_f32(f.y, M[h], S[h], rS[h]));
+                            __half2 pr = __floats2half2_rn(prob_f32(f.x, M[h], nMl[h], S[h], rS[h]), prob_f32(f.y, M[h], nMl[h], S[h], rS[h]));
                             if (tt >= nt) pr = __float2half2_rn(0.f);        // tokens beyond the packed length belong to the window
                             else if (tt + 1 >= nt) pr = __halves2half2(__low2half(pr), __float2half_rn(0.f));
                             if (p.dbg_probs) {
@@ -1498,7 +1517,7 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
                         } else {
                             x = __half2float(__ldcg(p.w.lg + (int64_t)(uq0 + h) * p.w.ld + s.tv + l0 + lane));
                         }
-                        const __half pr = __float2half_rn(prob_f32(x, M[h], S[h], rS[h]));
+                        const __half pr = __float2half_rn(prob_f32(x, M[h], nMl[h], S[h], rS[h]));
                         if (p.dbg_probs) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + s.tv + l0 + lane] = pr;
                         pl[h] = __half2float(pr);
                     }
@@ -1556,7 +1575,7 @@ sv_kernel(const KIVI_PARAM_QUAL AttnParams p)
                 #pragma unroll
                 for (int h = 0; h < G; ++h) {
                     const float x = __half2float(__ldcg(p.w.lg + (int64_t)(uq0 + h) * p.w.ld + s.T - 1));
-                    const __half prh = __float2half_rn(prob_f32(x, M[h], S[h], rS[h]));
+                    const __half prh = __float2half_rn(prob_f32(x, M[h], nMl[h], S[h], rS[h]));
                     if (p.dbg_probs && lane == 0) p.dbg_probs[(int64_t)(uq0 + h) * p.dbg_stride + s.T - 1] = prh;
                     const float pr = __half2float(prh);
                     orr[h][0] = fmaf(pr, v01.x, orr[h][0]); orr[h][1] = fmaf(pr, v01.y, orr[h][1]);
