@@ -28,6 +28,8 @@ CASES = [  # n_units, n_b, n_w, w_cap
     (1024, 31, 2, 2368),       # cfg 2 q.K^T
     (512, 63, 9, 2368),        # cfg 3
     (128, 511, 5, 2368),       # cfg 4: few long units
+    (128, 511, 5, 1776),       # cfg 4 as launched: 148 CTAs x 12 warps (kivi_attn.cuh WarpsPerCta<4, 4>)
+    (512, 63, 9, 1776),
     (8192, 31, 9, 2368),       # cfg 5 on one GPU: the 64-bit arithmetic path
     (3, 0, 2, 2368),           # tiny: nothing packed yet, more warps than items
     (1, 0, 0, 2368),           # one unit, only the new token
